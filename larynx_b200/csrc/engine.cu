@@ -1,0 +1,944 @@
+// engine.cu — model objects, per-call contexts and the C ABI of libb200tts.so (include/b200tts.h).
+//
+// Host orchestration of the hot path:
+//   glow encode  : glow_tts/models.py:118-140 (TextEncoder) + :323-331 (durations)
+//   glow decode  : glow_tts/models.py:335-349 (expand + noise) + :191-209 (FlowSpecDecoder reverse)
+//   hifigan infer: hifi_gan/models.py:186-202 (Generator.forward) + larynx/audio.py:118-125
+//   tts finish   : larynx/__init__.py:229-257 (_sentence_task) with the numpy mel glue on device
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace b2;
+
+// ------------------------------------------------------------------------------------------------
+// packed weight blob (written by larynx_b200/pack.py)
+// ------------------------------------------------------------------------------------------------
+#pragma pack(push, 1)
+struct BlobHeader {
+  char magic[8];  // "B2TTSBLB"
+  uint32_t version;
+  uint32_t kind;  // 1 = glow, 2 = hifigan
+  uint32_t n_tensors;
+  uint32_t n_cfg;
+  int32_t cfg[64];
+  uint64_t total_bytes;
+};
+struct BlobEntry {
+  char name[64];
+  uint64_t offset;  // bytes from blob start, 256-byte aligned
+  uint64_t numel;
+  uint32_t dtype;  // 0 = f32
+  uint32_t reserved;
+};
+#pragma pack(pop)
+
+struct Weights {
+  int device = 0;
+  void* dev = nullptr;
+  size_t nbytes = 0;
+  std::map<std::string, std::pair<const float*, size_t>> t;
+  int32_t cfg[64];
+  int n_cfg = 0;
+
+  void load(const void* blob, size_t nbytes_, int device_, uint32_t kind) {
+    B2_CHECK(nbytes_ >= sizeof(BlobHeader), "blob too small");
+    device = device_;
+    B2_CUDA(cudaSetDevice(device));
+    // the header/table may live in device memory: stage the front of the blob on the host
+    BlobHeader h;
+    B2_CUDA(cudaMemcpy(&h, blob, sizeof(h), cudaMemcpyDefault));
+    B2_CHECK(memcmp(h.magic, "B2TTSBLB", 8) == 0, "bad blob magic");
+    B2_CHECK(h.version == 1, "unsupported blob version");
+    B2_CHECK(h.kind == kind, "blob is for a different model kind");
+    B2_CHECK(h.total_bytes == nbytes_, "blob size mismatch");
+    B2_CHECK(h.n_tensors < 100000, "implausible tensor count");
+    std::vector<BlobEntry> table(h.n_tensors);
+    B2_CHECK(sizeof(BlobHeader) + sizeof(BlobEntry) * (size_t)h.n_tensors <= nbytes_, "blob table truncated");
+    B2_CUDA(cudaMemcpy(table.data(), (const char*)blob + sizeof(BlobHeader), sizeof(BlobEntry) * h.n_tensors,
+                       cudaMemcpyDefault));
+    nbytes = nbytes_;
+    B2_CUDA(cudaMalloc(&dev, nbytes));
+    B2_CUDA(cudaMemcpy(dev, blob, nbytes, cudaMemcpyDefault));
+    memcpy(cfg, h.cfg, sizeof(cfg));
+    n_cfg = h.n_cfg;
+    for (auto& e : table) {
+      B2_CHECK(e.offset % 16 == 0 && e.offset + e.numel * 4 <= nbytes, "blob entry out of range");
+      char nm[65];
+      memcpy(nm, e.name, 64);
+      nm[64] = 0;
+      t[nm] = {reinterpret_cast<const float*>((const char*)dev + e.offset), (size_t)e.numel};
+    }
+  }
+  const float* get(const std::string& name, size_t numel) const {
+    auto it = t.find(name);
+    if (it == t.end()) throw Error("blob is missing tensor '" + name + "'");
+    if (it->second.second != numel) throw Error("tensor '" + name + "' has the wrong size");
+    return it->second.first;
+  }
+  ~Weights() {
+    if (dev) cudaFree(dev);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// models
+// ------------------------------------------------------------------------------------------------
+struct ConvW {
+  const float* w = nullptr;
+  const float* b = nullptr;
+  int cin = 0, cout = 0, k = 1;
+};
+
+struct GlowFlow {
+  ConvW start, end;
+  ConvW in[8], rs[8];
+  const float *inv = nullptr, *an_bias = nullptr, *an_scale = nullptr;
+};
+struct GlowEnc {
+  ConvW qkv, o, ffn1, ffn2;
+  const float *rel_k, *rel_v, *ln1g, *ln1b, *ln2g, *ln2b;
+};
+
+struct b200tts_glow {
+  Weights W;
+  int V, H, F, Fd, K, n_heads, n_layers, window, mel, n_blocks, kd, dil_rate, n_block_layers, n_sqz, n_split, Hd;
+  const float* emb;
+  ConvW pre_conv[3], pre_proj, proj_m, dp1, dp2;
+  const float *pre_lng[3], *pre_lnb[3], *dp_ln1g, *dp_ln1b, *dp_ln2g, *dp_ln2b, *dp_pw, *dp_pb;
+  std::vector<GlowEnc> enc;
+  std::vector<GlowFlow> flow;
+};
+
+struct HifiRB {
+  ConvW c1[3], c2[3];
+  int k = 3, ndil = 3, dil[3] = {1, 3, 5};
+};
+struct b200tts_hifigan {
+  Weights W;
+  int resblock, n_ups, C0, n_kernels, mel, hop;
+  int up_rate[8], up_k[8];
+  ConvW conv_pre, conv_post, ups[8];
+  std::vector<HifiRB> rb;  // [n_ups * n_kernels]
+};
+
+static ConvW conv_w(const Weights& W, const std::string& name, int cin, int cout, int k, int mult = 1) {
+  ConvW c;
+  c.cin = cin;
+  c.cout = cout;
+  c.k = k;
+  c.w = W.get(name + ".w", (size_t)cin * cout * k * mult);
+  c.b = W.get(name + ".b", cout);
+  return c;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-call context
+// ------------------------------------------------------------------------------------------------
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, off = 0;
+  void reserve(size_t bytes) {
+    off = 0;
+    if (bytes <= cap) return;
+    if (base) B2_CUDA(cudaFree(base));
+    base = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + (1 << 20);
+    B2_CUDA(cudaMalloc((void**)&base, want));
+    cap = want;
+  }
+  template <typename T>
+  T* take(size_t n) {
+    size_t bytes = (n * sizeof(T) + 255) & ~(size_t)255;
+    B2_CHECK(off + bytes <= cap, "workspace arena overflow");
+    T* p = reinterpret_cast<T*>(base + off);
+    off += bytes;
+    return p;
+  }
+  static size_t pad(size_t n, size_t elt) { return (n * elt + 255) & ~(size_t)255; }
+  ~Arena() {
+    if (base) cudaFree(base);
+  }
+};
+
+struct b200tts_call {
+  int device = 0;
+  cudaStream_t stream = nullptr, aux[2] = {nullptr, nullptr};
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, fork = nullptr, join[2] = {nullptr, nullptr};
+  long long launches = 0;
+  float last_ms = 0.f;
+  int debug = 0;
+  Arena enc, dec, voc, stg;
+  // state carried from encode to decode
+  const b200tts_glow* enc_model = nullptr;
+  int batch = 0, max_tx = 0, tx_ld = 0, ty_max = 0;
+  std::vector<int> y_len_h;
+  int *xlen_d = nullptr, *ylen_d = nullptr, *sqlen_d = nullptr, *wceil_d = nullptr, *cum_d = nullptr;
+  float *logw_d = nullptr, *xm_d = nullptr;
+  // decode state
+  int *idx_d = nullptr, idx_ld = 0;
+  float* taps_d = nullptr;
+  int tq_ld = 0;
+  float* state_d = nullptr;
+};
+
+static thread_local std::string g_err;
+static int fail(const std::exception& e) {
+  g_err = e.what();
+  return 1;
+}
+#define B2_API_BEGIN try {
+#define B2_API_END \
+  }                \
+  catch (const std::exception& e) { return fail(e); } \
+  return 0;
+
+static bool is_device_ptr(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+struct Timer {
+  b200tts_call* c;
+  explicit Timer(b200tts_call* c_) : c(c_) { B2_CUDA(cudaEventRecord(c->ev0, c->stream)); }
+  void stop_and_sync() {
+    B2_CUDA(cudaEventRecord(c->ev1, c->stream));
+    B2_CUDA(cudaEventSynchronize(c->ev1));
+    B2_CUDA(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+  }
+};
+
+static void conv(b200tts_call* c, ConvParams& p, const ConvW& w, int batch, int Lmax, cudaStream_t s) {
+  p.w = w.w;
+  p.bias = w.b;
+  p.Cin = w.cin;
+  p.Cout = w.cout;
+  p.K = w.k;
+  c->launches += launch_conv1d(p, batch, Lmax, s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// GlowTTS
+// ------------------------------------------------------------------------------------------------
+static void glow_bind(b200tts_glow* m) {
+  const Weights& W = m->W;
+  const int32_t* c = W.cfg;
+  B2_CHECK(W.n_cfg >= 16, "glow blob config too short");
+  m->V = c[0]; m->H = c[1]; m->F = c[2]; m->Fd = c[3]; m->K = c[4]; m->n_heads = c[5]; m->n_layers = c[6];
+  m->window = c[7]; m->mel = c[8]; m->n_blocks = c[9]; m->kd = c[10]; m->dil_rate = c[11];
+  m->n_block_layers = c[12]; m->n_sqz = c[13]; m->n_split = c[14]; m->Hd = c[15];
+  B2_CHECK(m->n_split == 4 && m->n_sqz == 2, "only n_split=4, n_sqz=2 voices are supported");
+  B2_CHECK(m->n_block_layers <= 8, "too many WN layers");
+  B2_CHECK(m->H % 8 == 0 && m->Hd % 8 == 0 && m->mel % 8 == 0 && m->F % 8 == 0 && m->Fd % 8 == 0, "channel counts must be multiples of 8");
+  const int H = m->H, mel = m->mel, C = mel * m->n_sqz, Hd = m->Hd;
+  m->emb = W.get("emb", (size_t)m->V * H);
+  for (int i = 0; i < 3; ++i) {
+    std::string s = "pre.conv" + std::to_string(i);
+    m->pre_conv[i] = conv_w(W, s, H, H, 5);
+    m->pre_lng[i] = W.get("pre.ln" + std::to_string(i) + ".g", H);
+    m->pre_lnb[i] = W.get("pre.ln" + std::to_string(i) + ".b", H);
+  }
+  m->pre_proj = conv_w(W, "pre.proj", H, H, 1);
+  m->enc.resize(m->n_layers);
+  const int dk = H / m->n_heads, nrel = 2 * m->window + 1;
+  for (int i = 0; i < m->n_layers; ++i) {
+    std::string s = "enc" + std::to_string(i);
+    GlowEnc& e = m->enc[i];
+    e.qkv = conv_w(W, s + ".qkv", H, 3 * H, 1);
+    e.o = conv_w(W, s + ".o", H, H, 1);
+    e.ffn1 = conv_w(W, s + ".ffn1", H, m->F, m->K);
+    e.ffn2 = conv_w(W, s + ".ffn2", m->F, H, m->K);
+    e.rel_k = W.get(s + ".rel_k", (size_t)nrel * dk);
+    e.rel_v = W.get(s + ".rel_v", (size_t)nrel * dk);
+    e.ln1g = W.get(s + ".ln1.g", H); e.ln1b = W.get(s + ".ln1.b", H);
+    e.ln2g = W.get(s + ".ln2.g", H); e.ln2b = W.get(s + ".ln2.b", H);
+  }
+  m->proj_m = conv_w(W, "proj_m", H, mel, 1);
+  m->dp1 = conv_w(W, "dp.conv1", H, m->Fd, m->K);
+  m->dp2 = conv_w(W, "dp.conv2", m->Fd, m->Fd, m->K);
+  m->dp_ln1g = W.get("dp.ln1.g", m->Fd); m->dp_ln1b = W.get("dp.ln1.b", m->Fd);
+  m->dp_ln2g = W.get("dp.ln2.g", m->Fd); m->dp_ln2b = W.get("dp.ln2.b", m->Fd);
+  m->dp_pw = W.get("dp.proj.w", m->Fd);
+  m->dp_pb = W.get("dp.proj.b", 1);
+  m->flow.resize(m->n_blocks);
+  for (int b = 0; b < m->n_blocks; ++b) {
+    std::string s = "flow" + std::to_string(b);
+    GlowFlow& f = m->flow[b];
+    f.start = conv_w(W, s + ".start", C / 2, Hd, 1);
+    f.end = conv_w(W, s + ".end", Hd, C, 1);
+    for (int l = 0; l < m->n_block_layers; ++l) {
+      f.in[l] = conv_w(W, s + ".in" + std::to_string(l), Hd, 2 * Hd, m->kd);
+      f.rs[l] = conv_w(W, s + ".rs" + std::to_string(l), Hd, l < m->n_block_layers - 1 ? 2 * Hd : Hd, 1);
+    }
+    f.inv = W.get(s + ".inv", 16);
+    f.an_bias = W.get(s + ".an_bias", C);
+    f.an_scale = W.get(s + ".an_scale", C);
+  }
+}
+
+static void glow_encode_impl(const b200tts_glow* m, b200tts_call* c, const int64_t* ids, const int32_t* x_len,
+                             int batch, int max_tx, float length_scale, int32_t* y_len_out) {
+  B2_CHECK(batch > 0 && max_tx > 0, "empty batch");
+  B2_CHECK(m->W.device == c->device, "model and call live on different devices");
+  B2_CUDA(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  const int H = m->H, F = m->F, Fd = m->Fd, mel = m->mel;
+  const int ld = round_up(max_tx, 32);
+  const long long B = batch;
+  // ---- workspace
+  size_t need = 0;
+  need += Arena::pad(B * max_tx, 8) + 3 * Arena::pad(B, 4) + 2 * Arena::pad(B * max_tx, 4) + Arena::pad(B * max_tx, 4);
+  const size_t act = (size_t)B * ld;
+  need += Arena::pad(act * H, 4) * 4 + Arena::pad(act * 3 * H, 4) + Arena::pad(act * F, 4) +
+          Arena::pad(act * Fd, 4) * 2 + Arena::pad(act * mel, 4);
+  c->enc.reserve(need + 4096);
+  long long* ids_d = c->enc.take<long long>(B * max_tx);
+  c->xlen_d = c->enc.take<int>(B);
+  c->ylen_d = c->enc.take<int>(B);
+  c->sqlen_d = c->enc.take<int>(B);
+  c->wceil_d = c->enc.take<int>(B * max_tx);
+  c->cum_d = c->enc.take<int>(B * max_tx);
+  c->logw_d = c->enc.take<float>(B * max_tx);
+  float* X = c->enc.take<float>(act * H);
+  float* A = c->enc.take<float>(act * H);
+  float* Bf = c->enc.take<float>(act * H);
+  float* ATT = c->enc.take<float>(act * H);
+  float* QKV = c->enc.take<float>(act * 3 * H);
+  float* FF = c->enc.take<float>(act * F);
+  float* D1 = c->enc.take<float>(act * Fd);
+  float* D2 = c->enc.take<float>(act * Fd);
+  c->xm_d = c->enc.take<float>(act * mel);
+
+  Timer tm(c);
+  B2_CUDA(cudaMemcpyAsync(ids_d, ids, sizeof(long long) * B * max_tx, cudaMemcpyDefault, s));
+  B2_CUDA(cudaMemcpyAsync(c->xlen_d, x_len, sizeof(int) * B, cudaMemcpyDefault, s));
+  const int* lens = c->xlen_d;
+
+  auto mk = [&](const float* x, int cin_rows, float* y, int cout_rows) {
+    ConvParams p;
+    p.x = x; p.x_bs = (long long)cin_rows * ld; p.x_ld = ld;
+    p.y = y; p.y_bs = (long long)cout_rows * ld; p.y_ld = ld;
+    p.lens = lens; p.len_mul = 1; p.Lin = max_tx;
+    return p;
+  };
+  // embedding * sqrt(H)                                         models.py:119-121
+  launch_embed(ids_d, lens, batch, max_tx, m->emb, m->V, H, X, (long long)H * ld, ld, s);
+  c->launches++;
+  // prenet: 3 x (conv k5 -> LN -> ReLU), 1x1 proj + residual   layers.py:73-80
+  {
+    const float* h = X;
+    float* bufs[2] = {A, Bf};
+    for (int i = 0; i < 3; ++i) {
+      float* o = bufs[i & 1];
+      ConvParams p = mk(h, H, o, H);
+      p.pad_left = 2;
+      conv(c, p, m->pre_conv[i], batch, max_tx, s);
+      launch_layernorm(o, nullptr, m->pre_lng[i], m->pre_lnb[i], o, (long long)H * ld, ld, H, lens, batch, max_tx, 0,
+                       1, s);
+      c->launches++;
+      h = o;
+    }
+    ConvParams p = mk(h, H, X, H);
+    p.res = X; p.res_bs = (long long)H * ld; p.res_ld = ld;
+    conv(c, p, m->pre_proj, batch, max_tx, s);
+  }
+  // encoder layers                                              attentions.py:62-74
+  for (int i = 0; i < m->n_layers; ++i) {
+    const GlowEnc& e = m->enc[i];
+    ConvParams p = mk(X, H, QKV, 3 * H);
+    conv(c, p, e.qkv, batch, max_tx, s);
+    launch_rel_attention(QKV, (long long)3 * H * ld, ld, H, m->n_heads, e.rel_k, e.rel_v, m->window, lens, batch,
+                         max_tx, ATT, (long long)H * ld, ld, s);
+    c->launches++;
+    p = mk(ATT, H, A, H);
+    conv(c, p, e.o, batch, max_tx, s);
+    launch_layernorm(X, A, e.ln1g, e.ln1b, X, (long long)H * ld, ld, H, lens, batch, max_tx, 0, 0, s);
+    c->launches++;
+    p = mk(X, H, FF, F);
+    p.pad_left = m->K / 2; p.act = ACT_RELU;
+    conv(c, p, e.ffn1, batch, max_tx, s);
+    p = mk(FF, F, A, H);
+    p.pad_left = m->K / 2;
+    conv(c, p, e.ffn2, batch, max_tx, s);
+    launch_layernorm(X, A, e.ln2g, e.ln2b, X, (long long)H * ld, ld, H, lens, batch, max_tx, 0, 0, s);
+    c->launches++;
+  }
+  // proj_m                                                      models.py:133
+  {
+    ConvParams p = mk(X, H, c->xm_d, mel);
+    conv(c, p, m->proj_m, batch, max_tx, s);
+  }
+  // duration predictor                                          models.py:39-49
+  {
+    ConvParams p = mk(X, H, D1, Fd);
+    p.pad_left = m->K / 2;
+    conv(c, p, m->dp1, batch, max_tx, s);
+    launch_layernorm(D1, nullptr, m->dp_ln1g, m->dp_ln1b, D1, (long long)Fd * ld, ld, Fd, lens, batch, max_tx, 1, 0, s);
+    p = mk(D1, Fd, D2, Fd);
+    p.pad_left = m->K / 2;
+    conv(c, p, m->dp2, batch, max_tx, s);
+    launch_layernorm(D2, nullptr, m->dp_ln2g, m->dp_ln2b, D2, (long long)Fd * ld, ld, Fd, lens, batch, max_tx, 1, 0, s);
+    launch_duration(D2, (long long)Fd * ld, ld, Fd, m->dp_pw, m->dp_pb, lens, batch, max_tx, length_scale, m->n_sqz,
+                    c->logw_d, c->wceil_d, c->cum_d, c->ylen_d, s);
+    c->launches += 3;
+  }
+  c->y_len_h.resize(batch);
+  B2_CUDA(cudaMemcpyAsync(c->y_len_h.data(), c->ylen_d, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
+  tm.stop_and_sync();
+  c->enc_model = m;
+  c->batch = batch;
+  c->max_tx = max_tx;
+  c->tx_ld = ld;
+  c->ty_max = 0;
+  for (int b = 0; b < batch; ++b) {
+    c->ty_max = std::max(c->ty_max, c->y_len_h[b]);
+    if (y_len_out) y_len_out[b] = c->y_len_h[b];
+  }
+  c->idx_d = nullptr;
+}
+
+// Runs expand+noise+flow on c->stream.  Leaves the un-squeezed result in the squeezed state buffer
+// (c->state_d) and returns it; the caller launches the unsqueeze epilogue it needs.
+static void glow_flow_impl(const b200tts_glow* m, b200tts_call* c, float noise_scale, const float* eps, int eps_ld,
+                           uint64_t seed, size_t extra_bytes) {
+  B2_CHECK(c->enc_model == m, "b200tts_glow_decode must follow b200tts_glow_encode with the same model and call");
+  cudaStream_t s = c->stream;
+  const int batch = c->batch, mel = m->mel, C = mel * m->n_sqz, Hd = m->Hd;
+  const long long B = batch;
+  const int Ty = c->ty_max;
+  const int Tq = Ty / m->n_sqz;
+  const int ldq = round_up(std::max(Tq, 1), 32);
+  c->tq_ld = ldq;
+  c->idx_ld = round_up(std::max(Ty, 1), 32);
+  const bool eps_host = eps && !is_device_ptr(eps);
+  size_t need = Arena::pad(B * c->idx_ld, 4) + Arena::pad((size_t)B * C * ldq, 4) + 3 * Arena::pad((size_t)B * Hd * ldq, 4);
+  if (eps_host) need += Arena::pad((size_t)B * mel * eps_ld, 4);
+  if (c->debug) need += Arena::pad((size_t)m->n_blocks * B * C * ldq, 4);
+  c->dec.reserve(need + extra_bytes + 4096);
+  c->idx_d = c->dec.take<int>(B * c->idx_ld);
+  float* S = c->dec.take<float>((size_t)B * C * ldq);
+  float* Hh = c->dec.take<float>((size_t)B * Hd * ldq);
+  float* ACT = c->dec.take<float>((size_t)B * Hd * ldq);
+  float* SK = c->dec.take<float>((size_t)B * Hd * ldq);
+  const float* eps_d = eps;
+  if (eps_host) {
+    B2_CHECK(eps_ld >= Ty, "eps_ld smaller than the longest item");
+    float* e = c->dec.take<float>((size_t)B * mel * eps_ld);
+    B2_CUDA(cudaMemcpyAsync(e, eps, sizeof(float) * B * mel * eps_ld, cudaMemcpyHostToDevice, s));
+    eps_d = e;
+  }
+  c->taps_d = c->debug ? c->dec.take<float>((size_t)m->n_blocks * B * C * ldq) : nullptr;
+  c->state_d = S;
+
+  launch_align_index(c->cum_d, c->xlen_d, c->ylen_d, batch, c->max_tx, c->idx_d, c->idx_ld, c->sqlen_d, m->n_sqz, s);
+  c->launches++;
+  if (Ty <= 0) return;
+  launch_expand_squeeze(c->xm_d, (long long)mel * c->tx_ld, c->tx_ld, c->idx_d, c->idx_ld, c->ylen_d, eps_d,
+                        (long long)mel * eps_ld, eps_ld, noise_scale, seed, mel, m->n_sqz, S, (long long)C * ldq, ldq,
+                        batch, Ty, s);
+  c->launches++;
+  const int* lens = c->sqlen_d;
+  auto mk = [&](const float* x, int cin_rows, float* y, int cout_rows) {
+    ConvParams p;
+    p.x = x; p.x_bs = (long long)cin_rows * ldq; p.x_ld = ldq;
+    p.y = y; p.y_bs = (long long)cout_rows * ldq; p.y_ld = ldq;
+    p.lens = lens; p.len_mul = 1; p.Lin = Tq;
+    return p;
+  };
+  for (int blk = m->n_blocks - 1; blk >= 0; --blk) {
+    const GlowFlow& f = m->flow[blk];
+    // CouplingBlock reverse                                     attentions.py:119-142
+    ConvParams p = mk(S, C, Hh, Hd);  // start reads x0 = state[:, :C/2]
+    conv(c, p, f.start, batch, Tq, s);
+    for (int l = 0; l < m->n_block_layers; ++l) {  // WN       layers.py:138-162
+      int dil = 1;
+      for (int j = 0; j < l; ++j) dil *= m->dil_rate;
+      p = mk(Hh, Hd, ACT, Hd);
+      p.dil = dil; p.pad_left = (m->kd * dil - dil) / 2; p.epi = EPI_GATE;
+      conv(c, p, f.in[l], batch, Tq, s);
+      p = mk(ACT, Hd, Hh, Hd);
+      p.epi = EPI_RESSKIP; p.aux = SK; p.aux_bs = (long long)Hd * ldq; p.aux_ld = ldq;
+      p.split = l < m->n_block_layers - 1 ? Hd : 0;
+      p.first = l == 0;
+      conv(c, p, f.rs[l], batch, Tq, s);
+    }
+    p = mk(SK, Hd, S, C);
+    p.epi = EPI_COUPLING; p.inv_w = f.inv; p.an_bias = f.an_bias; p.an_scale = f.an_scale; p.half = C / 2;
+    conv(c, p, f.end, batch, Tq, s);
+    if (c->taps_d)
+      B2_CUDA(cudaMemcpyAsync(c->taps_d + (size_t)blk * B * C * ldq, S, sizeof(float) * B * C * ldq,
+                              cudaMemcpyDeviceToDevice, s));
+  }
+}
+
+// copy a device [batch][rows][ld_d] result into a caller buffer [batch][rows][ld_o] (host or device)
+static void copy_out_2d(void* dst, int ld_o, const void* src, int ld_d, int rows_total, int width, size_t elt,
+                        cudaStream_t s) {
+  if (!dst || rows_total <= 0 || width <= 0) return;
+  B2_CUDA(cudaMemcpy2DAsync(dst, (size_t)ld_o * elt, src, (size_t)ld_d * elt, (size_t)width * elt, rows_total,
+                            cudaMemcpyDefault, s));
+}
+
+static void glow_decode_impl(const b200tts_glow* m, b200tts_call* c, float noise_scale, const float* eps, int eps_ld,
+                             uint64_t seed, float* mel_out, int mel_ld) {
+  B2_CUDA(cudaSetDevice(c->device));
+  const int batch = c->batch, mel = m->mel;
+  B2_CHECK(mel_out != nullptr, "mel_out is null");
+  B2_CHECK(mel_ld >= c->ty_max, "mel_ld smaller than the longest item");
+  Timer tm(c);
+  const bool out_dev = is_device_ptr(mel_out);
+  const size_t extra = out_dev ? 0 : Arena::pad((size_t)batch * mel * std::max(mel_ld, 1), 4);
+  glow_flow_impl(m, c, noise_scale, eps, eps_ld, seed, extra);
+  cudaStream_t s = c->stream;
+  float* dst = out_dev ? mel_out : c->dec.take<float>((size_t)batch * mel * std::max(mel_ld, 1));
+  launch_unsqueeze(c->state_d, (long long)mel * m->n_sqz * c->tq_ld, c->tq_ld, c->ylen_d, mel, m->n_sqz, dst,
+                   (long long)mel * mel_ld, mel_ld, nullptr, 0, 0, nullptr, batch, mel_ld, s);
+  c->launches++;
+  if (!out_dev && mel_ld > 0)
+    B2_CUDA(cudaMemcpyAsync(mel_out, dst, sizeof(float) * batch * mel * mel_ld, cudaMemcpyDeviceToHost, s));
+  tm.stop_and_sync();
+}
+
+// ------------------------------------------------------------------------------------------------
+// HiFi-GAN
+// ------------------------------------------------------------------------------------------------
+static void hifigan_bind(b200tts_hifigan* m) {
+  const Weights& W = m->W;
+  const int32_t* c = W.cfg;
+  B2_CHECK(W.n_cfg >= 40, "hifigan blob config too short");
+  m->resblock = c[0]; m->n_ups = c[1]; m->C0 = c[2]; m->n_kernels = c[3]; m->mel = c[4];
+  B2_CHECK(m->n_ups <= 8 && m->n_kernels == 3, "unsupported HiFi-GAN shape");
+  m->hop = 1;
+  for (int i = 0; i < m->n_ups; ++i) {
+    m->up_rate[i] = c[8 + i];
+    m->up_k[i] = c[16 + i];
+    B2_CHECK(m->up_k[i] == 2 * m->up_rate[i], "only k = 2*stride transposed convs are supported");
+    m->hop *= m->up_rate[i];
+  }
+  m->conv_pre = conv_w(W, "conv_pre", m->mel, m->C0, 7);
+  int ch = m->C0;
+  m->rb.resize(m->n_ups * m->n_kernels);
+  for (int i = 0; i < m->n_ups; ++i) {
+    const int cin = m->C0 >> i, cout = m->C0 >> (i + 1);
+    m->ups[i] = conv_w(W, "ups" + std::to_string(i), cin, cout, 2, m->up_rate[i]);
+    ch = cout;
+    B2_CHECK(ch % 8 == 0, "channel counts must be multiples of 8");
+    for (int j = 0; j < m->n_kernels; ++j) {
+      HifiRB& r = m->rb[i * m->n_kernels + j];
+      r.k = c[24 + j];
+      r.ndil = m->resblock == 1 ? 3 : 2;
+      std::string s = "rb" + std::to_string(i * m->n_kernels + j);
+      for (int d = 0; d < r.ndil; ++d) {
+        r.dil[d] = c[28 + j * 3 + d];
+        r.c1[d] = conv_w(W, s + ".c1_" + std::to_string(d), ch, ch, r.k);
+        if (m->resblock == 1) r.c2[d] = conv_w(W, s + ".c2_" + std::to_string(d), ch, ch, r.k);
+      }
+    }
+  }
+  m->conv_post.cin = ch; m->conv_post.cout = 1; m->conv_post.k = 7;
+  m->conv_post.w = W.get("conv_post.w", (size_t)ch * 7);
+  m->conv_post.b = W.get("conv_post.b", 1);
+}
+
+// mel_d: device [batch][mel][mel_ld]; frames_d device [batch]; results -> pcm buffers (host or device)
+static void hifigan_run(const b200tts_hifigan* m, b200tts_call* c, const float* mel_d, int mel_ld, const int* frames_d,
+                        const int* frames_h, int batch, float* pcm_f32, int16_t* pcm_i16, int pcm_ld) {
+  cudaStream_t s = c->stream;
+  const long long B = batch;
+  int Tmax = 0;
+  for (int b = 0; b < batch; ++b) Tmax = std::max(Tmax, frames_h[b]);
+  const int hop = m->hop;
+  B2_CHECK(pcm_ld >= Tmax * hop, "pcm_ld smaller than the longest item");
+  const int ld0 = round_up(std::max(Tmax, 1), 32);
+  // ---- workspace: conv_pre output + two alternating stage buffer sets of 7 activations each
+  size_t stage_max = 0;
+  {
+    int L = ld0;
+    for (int i = 0; i < m->n_ups; ++i) {
+      L *= m->up_rate[i];
+      stage_max = std::max(stage_max, (size_t)(m->C0 >> (i + 1)) * L);
+    }
+  }
+  const int Lout_ld = ld0 * hop;
+  size_t need = Arena::pad((size_t)B * m->C0 * ld0, 4) + 14 * Arena::pad(B * stage_max, 4) +
+                Arena::pad((size_t)B * Lout_ld, 4) + Arena::pad(B, 4) + Arena::pad((size_t)B * Lout_ld, 2);
+  c->voc.reserve(need + 4096);
+  float* P = c->voc.take<float>((size_t)B * m->C0 * ld0);
+  float* setb[2][7];
+  for (int a = 0; a < 2; ++a)
+    for (int j = 0; j < 7; ++j) setb[a][j] = c->voc.take<float>(B * stage_max);
+  float* pcm_d = c->voc.take<float>((size_t)B * Lout_ld);
+  unsigned int* peak_d = c->voc.take<unsigned int>(B);
+  short* i16_d = c->voc.take<short>((size_t)B * Lout_ld);
+
+  if (Tmax > 0) {
+    B2_CUDA(cudaMemsetAsync(peak_d, 0, sizeof(unsigned int) * B, s));
+    // conv_pre                                                   hifi_gan/models.py:187
+    {
+      ConvParams p;
+      p.x = mel_d; p.x_bs = (long long)m->mel * mel_ld; p.x_ld = mel_ld;
+      p.y = P; p.y_bs = (long long)m->C0 * ld0; p.y_ld = ld0;
+      p.lens = frames_d; p.len_mul = 1; p.Lin = Tmax; p.pad_left = 3;
+      conv(c, p, m->conv_pre, batch, Tmax, s);
+    }
+    const float *in1 = P, *in2 = nullptr, *in3 = nullptr;
+    float in_div = 1.f;
+    int Lin_ld = ld0, len_mul = 1, cin = m->C0;
+    for (int i = 0; i < m->n_ups; ++i) {
+      const int u = m->up_rate[i], cout = m->C0 >> (i + 1);
+      const int Lld = Lin_ld * u;
+      float** bs_ = setb[i & 1];
+      float* U = bs_[0];
+      // x = leaky_relu(x, 0.1); x = ups[i](x)                    hifi_gan/models.py:189-190
+      {
+        ConvParams p;
+        p.x = in1; p.x2 = in2; p.x3 = in3; p.in_div = in_div;
+        p.x_bs = (long long)cin * Lin_ld; p.x_ld = Lin_ld;
+        p.pre = PRE_LRELU; p.pre_slope = 0.1f;
+        p.y = U; p.y_bs = (long long)cout * Lld; p.y_ld = Lld;
+        p.lens = frames_d; p.len_mul = len_mul; p.Lin = Tmax * len_mul;
+        p.n_phase = u; p.tpad = (m->up_k[i] - u) / 2;
+        conv(c, p, m->ups[i], batch, Tmax * len_mul, s);
+      }
+      len_mul *= u;
+      const int L = Tmax * len_mul;
+      // three resblocks on three streams                          hifi_gan/models.py:191-197
+      B2_CUDA(cudaEventRecord(c->fork, s));
+      for (int j = 0; j < m->n_kernels; ++j) {
+        cudaStream_t sj = j == 0 ? s : c->aux[j - 1];
+        if (j > 0) B2_CUDA(cudaStreamWaitEvent(sj, c->fork, 0));
+        const HifiRB& r = m->rb[i * m->n_kernels + j];
+        float* R = bs_[1 + j];
+        float* T = bs_[4 + j];
+        for (int d = 0; d < r.ndil; ++d) {
+          const float* xin = d == 0 ? U : R;
+          ConvParams p;
+          p.x = xin; p.x_bs = (long long)cout * Lld; p.x_ld = Lld;
+          p.pre = PRE_LRELU; p.pre_slope = 0.1f;
+          p.lens = frames_d; p.len_mul = len_mul; p.Lin = L;
+          p.dil = r.dil[d]; p.pad_left = (r.k * r.dil[d] - r.dil[d]) / 2;
+          if (m->resblock == 1) {
+            p.y = T; p.y_bs = (long long)cout * Lld; p.y_ld = Lld;
+            conv(c, p, r.c1[d], batch, L, sj);
+            ConvParams q;
+            q.x = T; q.x_bs = (long long)cout * Lld; q.x_ld = Lld;
+            q.pre = PRE_LRELU; q.pre_slope = 0.1f;
+            q.lens = frames_d; q.len_mul = len_mul; q.Lin = L;
+            q.dil = 1; q.pad_left = (r.k - 1) / 2;
+            q.y = R; q.y_bs = (long long)cout * Lld; q.y_ld = Lld;
+            q.res = xin; q.res_bs = (long long)cout * Lld; q.res_ld = Lld;
+            conv(c, q, r.c2[d], batch, L, sj);
+          } else {  // ResBlock2                                   hifi_gan/models.py:137-142
+            float* dst = (d & 1) ? R : T;  // ping-pong: conv input and output must differ
+            const float* src = d == 0 ? U : ((d & 1) ? T : R);
+            p.x = src;
+            p.y = dst; p.y_bs = (long long)cout * Lld; p.y_ld = Lld;
+            p.res = src; p.res_bs = (long long)cout * Lld; p.res_ld = Lld;
+            conv(c, p, r.c1[d], batch, L, sj);
+          }
+        }
+        if (j > 0) {
+          B2_CUDA(cudaEventRecord(c->join[j - 1], sj));
+          B2_CUDA(cudaStreamWaitEvent(s, c->join[j - 1], 0));
+        }
+      }
+      // the resblock result buffer: ResBlock1 -> R; ResBlock2 with ndil=2 -> last dst = R (d=1)
+      in1 = bs_[1]; in2 = bs_[2]; in3 = bs_[3];
+      in_div = (float)m->n_kernels;
+      Lin_ld = Lld;
+      cin = cout;
+    }
+    // leaky_relu(0.01) -> conv_post -> tanh                       hifi_gan/models.py:198-200
+    launch_conv_post(in1, in2, in3, (long long)cin * Lin_ld, Lin_ld, in_div, 0.01f, m->conv_post.w, m->conv_post.b, cin,
+                     m->conv_post.k, frames_d, len_mul, batch, Tmax * len_mul, pcm_d, Lout_ld, peak_d, s);
+    c->launches++;
+    if (pcm_i16) {
+      launch_pcm_to_i16(pcm_d, Lout_ld, peak_d, frames_d, len_mul, batch, i16_d, Lout_ld, s);
+      c->launches++;
+    }
+    if (pcm_f32) {
+      launch_zero_tail(pcm_d, Lout_ld, Lout_ld, 1, frames_d, len_mul, batch, Lout_ld, s);
+      c->launches++;
+    }
+  } else {
+    B2_CUDA(cudaMemsetAsync(pcm_d, 0, sizeof(float) * B * Lout_ld, s));
+    B2_CUDA(cudaMemsetAsync(i16_d, 0, sizeof(short) * B * Lout_ld, s));
+  }
+  const int w = std::min(pcm_ld, Lout_ld);
+  copy_out_2d(pcm_f32, pcm_ld, pcm_d, Lout_ld, batch, w, sizeof(float), s);
+  copy_out_2d(pcm_i16, pcm_ld, i16_d, Lout_ld, batch, w, sizeof(short), s);
+}
+
+static void hifigan_infer_impl(const b200tts_hifigan* m, b200tts_call* c, const float* mel, const int32_t* frames,
+                               int batch, int mel_ld, float* pcm_f32, int16_t* pcm_i16, int pcm_ld) {
+  B2_CHECK(batch > 0, "empty batch");
+  B2_CHECK(m->W.device == c->device, "model and call live on different devices");
+  B2_CUDA(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  std::vector<int> fh(batch);
+  if (is_device_ptr(frames)) B2_CUDA(cudaMemcpy(fh.data(), frames, sizeof(int) * batch, cudaMemcpyDeviceToHost));
+  else memcpy(fh.data(), frames, sizeof(int) * batch);
+  int Tmax = 0;
+  for (int b = 0; b < batch; ++b) {
+    B2_CHECK(fh[b] >= 0 && fh[b] <= mel_ld, "frames[b] out of range");
+    Tmax = std::max(Tmax, fh[b]);
+  }
+  // stage inputs in the decode arena (the vocoder arena is reserved inside hifigan_run)
+  const bool mel_dev = is_device_ptr(mel);
+  c->stg.reserve(Arena::pad(batch, 4) + (mel_dev ? 0 : Arena::pad((size_t)batch * m->mel * std::max(mel_ld, 1), 4)) + 4096);
+  int* frames_d = c->stg.take<int>(batch);
+  Timer tm(c);
+  B2_CUDA(cudaMemcpyAsync(frames_d, fh.data(), sizeof(int) * batch, cudaMemcpyHostToDevice, s));
+  const float* mel_d = mel;
+  if (!mel_dev) {
+    float* md = c->stg.take<float>((size_t)batch * m->mel * std::max(mel_ld, 1));
+    if (mel_ld > 0)
+      B2_CUDA(cudaMemcpyAsync(md, mel, sizeof(float) * batch * m->mel * mel_ld, cudaMemcpyHostToDevice, s));
+    mel_d = md;
+  }
+  hifigan_run(m, c, mel_d, mel_ld, frames_d, fh.data(), batch, pcm_f32, pcm_i16, pcm_ld);
+  tm.stop_and_sync();
+}
+
+static void tts_finish_impl(const b200tts_glow* g, const b200tts_hifigan* v, b200tts_call* c, const b200tts_glue* glue,
+                            float noise_scale, const float* eps, int eps_ld, uint64_t seed, float* mel_out, int mel_ld,
+                            float* pcm_f32, int16_t* pcm_i16, int pcm_ld) {
+  B2_CHECK(glue != nullptr, "glue settings are required");
+  B2_CHECK(g->W.device == c->device && v->W.device == c->device, "models and call live on different devices");
+  B2_CHECK(g->mel == v->mel, "mel channel mismatch between the two models");
+  B2_CUDA(cudaSetDevice(c->device));
+  const int batch = c->batch, mel = g->mel;
+  const int Ty = c->ty_max;
+  const int gl_ld = round_up(std::max(Ty, 1), 32);
+  if (mel_out) B2_CHECK(mel_ld >= Ty, "mel_ld smaller than the longest item");
+  Timer tm(c);
+  const bool mel_host = mel_out && !is_device_ptr(mel_out);
+  size_t extra = Arena::pad((size_t)batch * mel * gl_ld, 4);
+  if (mel_host) extra += Arena::pad((size_t)batch * mel * std::max(mel_ld, 1), 4);
+  glow_flow_impl(g, c, noise_scale, eps, eps_ld, seed, extra);
+  cudaStream_t s = c->stream;
+  float* glued = c->dec.take<float>((size_t)batch * mel * gl_ld);
+  float* mdst = nullptr;
+  if (mel_out) mdst = mel_host ? c->dec.take<float>((size_t)batch * mel * std::max(mel_ld, 1)) : mel_out;
+  const int width = std::max(mel_out ? mel_ld : 0, Ty);
+  launch_unsqueeze(c->state_d, (long long)mel * g->n_sqz * c->tq_ld, c->tq_ld, c->ylen_d, mel, g->n_sqz, mdst,
+                   (long long)mel * mel_ld, mel_ld, glued, (long long)mel * gl_ld, gl_ld, glue, batch, width, s);
+  c->launches++;
+  if (mel_host && mel_ld > 0)
+    B2_CUDA(cudaMemcpyAsync(mel_out, mdst, sizeof(float) * batch * mel * mel_ld, cudaMemcpyDeviceToHost, s));
+  hifigan_run(v, c, glued, gl_ld, c->ylen_d, c->y_len_h.data(), batch, pcm_f32, pcm_i16, pcm_ld);
+  tm.stop_and_sync();
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* b200tts_last_error(void) { return g_err.c_str(); }
+int b200tts_version(void) { return B200TTS_VERSION; }
+
+int b200tts_device_count(int* count) {
+  B2_API_BEGIN
+  B2_CHECK(count != nullptr, "null argument");
+  B2_CUDA(cudaGetDeviceCount(count));
+  B2_API_END
+}
+
+int b200tts_call_create(int device, b200tts_call** out) {
+  B2_API_BEGIN
+  B2_CHECK(out != nullptr, "null argument");
+  B2_CUDA(cudaSetDevice(device));
+  conv1d_init_attributes();
+  attention_init_attributes();
+  b200tts_call* c = new b200tts_call();
+  c->device = device;
+  B2_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    B2_CUDA(cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking));
+    B2_CUDA(cudaEventCreateWithFlags(&c->join[i], cudaEventDisableTiming));
+  }
+  B2_CUDA(cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming));
+  B2_CUDA(cudaEventCreate(&c->ev0));
+  B2_CUDA(cudaEventCreate(&c->ev1));
+  *out = c;
+  B2_API_END
+}
+
+int b200tts_call_destroy(b200tts_call* c) {
+  B2_API_BEGIN
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (int i = 0; i < 2; ++i) {
+    cudaStreamSynchronize(c->aux[i]);
+    cudaStreamDestroy(c->aux[i]);
+    cudaEventDestroy(c->join[i]);
+  }
+  cudaStreamDestroy(c->stream);
+  cudaEventDestroy(c->fork);
+  cudaEventDestroy(c->ev0);
+  cudaEventDestroy(c->ev1);
+  delete c;
+  B2_API_END
+}
+
+int b200tts_call_last_ms(b200tts_call* c, float* ms) {
+  B2_API_BEGIN
+  B2_CHECK(c && ms, "null argument");
+  *ms = c->last_ms;
+  B2_API_END
+}
+int b200tts_call_launches(b200tts_call* c, int64_t* n) {
+  B2_API_BEGIN
+  B2_CHECK(c && n, "null argument");
+  *n = c->launches;
+  B2_API_END
+}
+int b200tts_call_stream(b200tts_call* c, void** stream) {
+  B2_API_BEGIN
+  B2_CHECK(c && stream, "null argument");
+  *stream = (void*)c->stream;
+  B2_API_END
+}
+int b200tts_call_set_debug(b200tts_call* c, int on) {
+  B2_API_BEGIN
+  B2_CHECK(c, "null argument");
+  c->debug = on;
+  B2_API_END
+}
+
+int b200tts_glow_create(const void* blob, size_t nbytes, int device, b200tts_glow** out) {
+  B2_API_BEGIN
+  B2_CHECK(blob && out, "null argument");
+  std::unique_ptr<b200tts_glow> m(new b200tts_glow());
+  m->W.load(blob, nbytes, device, 1);
+  glow_bind(m.get());
+  *out = m.release();
+  B2_API_END
+}
+int b200tts_glow_destroy(b200tts_glow* m) {
+  B2_API_BEGIN
+  if (m) {
+    cudaSetDevice(m->W.device);
+    delete m;
+  }
+  B2_API_END
+}
+int b200tts_glow_info(const b200tts_glow* m, int32_t* num_symbols, int32_t* mel_channels, int32_t* n_sqz) {
+  B2_API_BEGIN
+  B2_CHECK(m, "null argument");
+  if (num_symbols) *num_symbols = m->V;
+  if (mel_channels) *mel_channels = m->mel;
+  if (n_sqz) *n_sqz = m->n_sqz;
+  B2_API_END
+}
+
+int b200tts_glow_encode(const b200tts_glow* m, b200tts_call* call, const int64_t* ids, const int32_t* x_len, int batch,
+                        int max_tx, float length_scale, int32_t* y_len_out) {
+  B2_API_BEGIN
+  B2_CHECK(m && call && ids && x_len, "null argument");
+  if (!is_device_ptr(x_len))
+    for (int b = 0; b < batch; ++b) B2_CHECK(x_len[b] >= 0 && x_len[b] <= max_tx, "x_len[b] out of range");
+  glow_encode_impl(m, call, ids, x_len, batch, max_tx, length_scale, y_len_out);
+  B2_API_END
+}
+
+int b200tts_glow_decode(const b200tts_glow* m, b200tts_call* call, float noise_scale, const float* eps, int eps_ld,
+                        uint64_t seed, float* mel_out, int mel_ld) {
+  B2_API_BEGIN
+  B2_CHECK(m && call, "null argument");
+  glow_decode_impl(m, call, noise_scale, eps, eps_ld, seed, mel_out, mel_ld);
+  B2_API_END
+}
+
+int b200tts_glow_alignment(const b200tts_glow* m, b200tts_call* c, float* logw, int32_t* w_ceil, int32_t* idx,
+                           int idx_ld) {
+  B2_API_BEGIN
+  B2_CHECK(m && c && c->enc_model == m, "no encode state on this call");
+  B2_CUDA(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  const size_t n = (size_t)c->batch * c->max_tx;
+  if (logw) B2_CUDA(cudaMemcpyAsync(logw, c->logw_d, sizeof(float) * n, cudaMemcpyDefault, s));
+  if (w_ceil) B2_CUDA(cudaMemcpyAsync(w_ceil, c->wceil_d, sizeof(int) * n, cudaMemcpyDefault, s));
+  if (idx) {
+    B2_CHECK(c->idx_d != nullptr, "alignment indices exist only after decode");
+    B2_CHECK(idx_ld >= c->ty_max, "idx_ld smaller than the longest item");
+    copy_out_2d(idx, idx_ld, c->idx_d, c->idx_ld, c->batch, std::min(idx_ld, c->idx_ld), sizeof(int), s);
+  }
+  B2_CUDA(cudaStreamSynchronize(s));
+  B2_API_END
+}
+
+int b200tts_glow_flow_tap(const b200tts_glow* m, b200tts_call* c, int blk, float* out, int ld) {
+  B2_API_BEGIN
+  B2_CHECK(m && c && out, "null argument");
+  B2_CHECK(c->taps_d != nullptr, "flow taps were not recorded (set debug before decode)");
+  B2_CHECK(blk >= 0 && blk < m->n_blocks, "block index out of range");
+  B2_CUDA(cudaSetDevice(c->device));
+  const int C = m->mel * m->n_sqz;
+  const int Tq = c->ty_max / m->n_sqz;
+  B2_CHECK(ld >= Tq, "ld too small");
+  copy_out_2d(out, ld, c->taps_d + (size_t)blk * c->batch * C * c->tq_ld, c->tq_ld, c->batch * C, Tq, sizeof(float),
+              c->stream);
+  B2_CUDA(cudaStreamSynchronize(c->stream));
+  B2_API_END
+}
+
+int b200tts_hifigan_create(const void* blob, size_t nbytes, int device, b200tts_hifigan** out) {
+  B2_API_BEGIN
+  B2_CHECK(blob && out, "null argument");
+  std::unique_ptr<b200tts_hifigan> m(new b200tts_hifigan());
+  m->W.load(blob, nbytes, device, 2);
+  hifigan_bind(m.get());
+  *out = m.release();
+  B2_API_END
+}
+int b200tts_hifigan_destroy(b200tts_hifigan* m) {
+  B2_API_BEGIN
+  if (m) {
+    cudaSetDevice(m->W.device);
+    delete m;
+  }
+  B2_API_END
+}
+int b200tts_hifigan_info(const b200tts_hifigan* m, int32_t* mel_channels, int32_t* hop) {
+  B2_API_BEGIN
+  B2_CHECK(m, "null argument");
+  if (mel_channels) *mel_channels = m->mel;
+  if (hop) *hop = m->hop;
+  B2_API_END
+}
+
+int b200tts_hifigan_infer(const b200tts_hifigan* m, b200tts_call* call, const float* mel, const int32_t* frames,
+                          int batch, int mel_ld, float* pcm_f32, int16_t* pcm_i16, int pcm_ld) {
+  B2_API_BEGIN
+  B2_CHECK(m && call && mel && frames, "null argument");
+  hifigan_infer_impl(m, call, mel, frames, batch, mel_ld, pcm_f32, pcm_i16, pcm_ld);
+  B2_API_END
+}
+
+int b200tts_tts_finish(const b200tts_glow* g, const b200tts_hifigan* v, b200tts_call* call, const b200tts_glue* glue,
+                       float noise_scale, const float* eps, int eps_ld, uint64_t seed, float* mel_out, int mel_ld,
+                       float* pcm_f32, int16_t* pcm_i16, int pcm_ld) {
+  B2_API_BEGIN
+  B2_CHECK(g && v && call, "null argument");
+  tts_finish_impl(g, v, call, glue, noise_scale, eps, eps_ld, seed, mel_out, mel_ld, pcm_f32, pcm_i16, pcm_ld);
+  B2_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,604 @@
+// kernels.cu — every non-conv kernel of the hot path + the conv launcher.
+#include <string.h>
+
+#include "conv1d.cuh"
+#include "kernels.cuh"
+
+namespace b2 {
+
+// ------------------------------------------------------------------------------------------------
+// conv launcher
+// ------------------------------------------------------------------------------------------------
+template <int BM, int BN, int TM, int TN>
+static void launch_cfg(const ConvParams& p, int batch, int Lmax, cudaStream_t s) {
+  using C = ConvCfg<BM, BN, TM, TN>;
+  dim3 grid((Lmax + BN - 1) / BN, (p.Cout + BM - 1) / BM, batch * p.n_phase);
+  conv1d_kernel<BM, BN, TM, TN><<<grid, C::NT, C::smem_bytes(p.K), s>>>(p);
+}
+
+template <int BM, int BN, int TM, int TN>
+static void set_attr() {
+  B2_CUDA(cudaFuncSetAttribute(conv1d_kernel<BM, BN, TM, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)ConvCfg<BM, BN, TM, TN>::smem_bytes(16)));
+}
+
+void conv1d_init_attributes() {
+  set_attr<64, 128, 8, 8>();
+  set_attr<64, 64, 8, 4>();
+  set_attr<32, 32, 4, 4>();
+}
+
+int launch_conv1d(const ConvParams& p, int batch, int Lmax, cudaStream_t stream) {
+  B2_CHECK(p.Cout % 4 == 0, "conv1d: Cout must be a multiple of 4");
+  B2_CHECK((p.K - 1) * p.dil <= CONV_HALO_MAX, "conv1d: receptive field too wide");
+  B2_CHECK(p.K <= 16, "conv1d: K too large");
+  B2_CHECK(p.n_phase == 1 || p.K == 2, "conv1d: transposed conv needs 2 polyphase taps");
+  if (Lmax <= 0 || batch <= 0) return 0;
+  auto ctas = [&](int bm, int bn) {
+    return (long long)((Lmax + bn - 1) / bn) * ((p.Cout + bm - 1) / bm) * batch * p.n_phase;
+  };
+  const bool paired = p.epi == EPI_COUPLING;  // needs TM % 4 == 0 (always true here)
+  (void)paired;
+  if (ctas(64, 128) >= 120 && p.Cout >= 64) launch_cfg<64, 128, 8, 8>(p, batch, Lmax, stream);
+  else if (ctas(64, 64) >= 120 && p.Cout >= 64) launch_cfg<64, 64, 8, 4>(p, batch, Lmax, stream);
+  else launch_cfg<32, 32, 4, 4>(p, batch, Lmax, stream);
+  B2_CUDA(cudaGetLastError());
+  return 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// embedding: x[b][c][t] = emb[ids[b][t]][c] * sqrt(H)           (glow_tts/models.py:119-120)
+// ------------------------------------------------------------------------------------------------
+__global__ void embed_kernel(const long long* __restrict__ ids, const int* __restrict__ lens, int max_tx,
+                             const float* __restrict__ emb, int n_vocab, int H, float scale, float* __restrict__ x,
+                             long long x_bs, int x_ld) {
+  const int b = blockIdx.z;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.y;
+  if (t >= lens[b]) return;
+  long long id = ids[(size_t)b * max_tx + t];
+  id = id < 0 ? 0 : (id >= n_vocab ? n_vocab - 1 : id);
+  x[(size_t)b * x_bs + (size_t)c * x_ld + t] = emb[(size_t)id * H + c] * scale;
+}
+
+void launch_embed(const long long* ids, const int* lens, int batch, int max_tx, const float* emb, int n_vocab, int H,
+                  float* x, long long x_bs, int x_ld, cudaStream_t s) {
+  dim3 grid((max_tx + 63) / 64, H, batch);
+  embed_kernel<<<grid, 64, 0, s>>>(ids, lens, max_tx, emb, n_vocab, H, sqrtf((float)H), x, x_bs, x_ld);
+  B2_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// channel LayerNorm  (glow_tts/layers.py:19-28): per (b,t) over channels, biased variance, eps 1e-4
+//   v = x (+ res); v = relu(v) if pre_relu; y = (v-mean)*rsqrt(var+eps)*gamma+beta; relu if post_relu
+// block = 32 time steps x 8 channel groups; each thread keeps its C/8 values in registers.
+// ------------------------------------------------------------------------------------------------
+constexpr int LN_MAXC = 256;
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ res,
+                                                        const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, float* __restrict__ y,
+                                                        long long bs, int ld, int C, const int* __restrict__ lens,
+                                                        int pre_relu, int post_relu, float eps) {
+  __shared__ float red[8][33];
+  const int b = blockIdx.y;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int t = blockIdx.x * 32 + tx;
+  const bool valid = t < lens[b];
+  const float* xb = x + (size_t)b * bs;
+  const float* rb = res ? res + (size_t)b * bs : nullptr;
+  float v[LN_MAXC / 8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXC / 8; ++i) {
+    const int c = ty + i * 8;
+    float a = 0.f;
+    if (valid && c < C) {
+      a = xb[(size_t)c * ld + t];
+      if (rb) a += rb[(size_t)c * ld + t];
+      if (pre_relu) a = fmaxf(a, 0.f);
+    }
+    v[i] = a;
+    s += a;
+  }
+  red[ty][tx] = s;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) tot += red[j][tx];
+  const float mean = tot / (float)C;
+  __syncthreads();
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXC / 8; ++i) {
+    const int c = ty + i * 8;
+    if (c < C) {
+      const float d = v[i] - mean;
+      q += d * d;
+    }
+  }
+  red[ty][tx] = q;
+  __syncthreads();
+  float qt = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) qt += red[j][tx];
+  const float rstd = rsqrtf(qt / (float)C + eps);
+  if (!valid) return;
+  float* yb = y + (size_t)b * bs;
+#pragma unroll
+  for (int i = 0; i < LN_MAXC / 8; ++i) {
+    const int c = ty + i * 8;
+    if (c < C) {
+      float o = (v[i] - mean) * rstd * gamma[c] + beta[c];
+      if (post_relu) o = fmaxf(o, 0.f);
+      yb[(size_t)c * ld + t] = o;
+    }
+  }
+}
+
+void launch_layernorm(const float* x, const float* res, const float* gamma, const float* beta, float* y, long long bs,
+                      int ld, int C, const int* lens, int batch, int Lmax, int pre_relu, int post_relu,
+                      cudaStream_t s) {
+  B2_CHECK(C <= LN_MAXC, "layernorm: too many channels");
+  dim3 grid((Lmax + 31) / 32, batch);
+  layernorm_kernel<<<grid, 256, 0, s>>>(x, res, gamma, beta, y, bs, ld, C, lens, pre_relu, post_relu, 1e-4f);
+  B2_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// relative-position multi-head self-attention (glow_tts/attentions.py:214-264), closed form:
+//   s[i][j] = (q_i.k_j + [|j-i|<=w] q_i.Ek[j-i+w]) / sqrt(dk);  p = softmax_j(s) over j < len
+//   o_i = sum_j p[i][j] v_j + sum_{|r|<=w} p[i][i+r] Ev[r+w]
+// (keys j >= len get -1e4 in the reference, i.e. exp underflows to exactly 0 in fp32 for valid rows)
+// qkv: [b][3*H][ld]: rows [0,H) = q, [H,2H) = k, [2H,3H) = v; head h owns channels h*dk..(h+1)*dk.
+// grid (ceil(T/QT), heads, batch); block 128.  Scores for QT queries x T keys live in smem.
+// ------------------------------------------------------------------------------------------------
+constexpr int ATT_QT = 8;
+constexpr int ATT_JT = 32;
+constexpr int ATT_DK_MAX = 96;
+constexpr int ATT_NT = 128;
+
+__global__ void __launch_bounds__(ATT_NT) rel_attention_kernel(const float* __restrict__ qkv, long long bs, int ld,
+                                                                int H, int dk, const float* __restrict__ emb_k,
+                                                                const float* __restrict__ emb_v, int window,
+                                                                const int* __restrict__ lens, float* __restrict__ out,
+                                                                long long out_bs, int out_ld, int Tpad) {
+  extern __shared__ float sm[];
+  float* qs = sm;                         // [dk][QT]
+  float* kv = qs + ATT_DK_MAX * ATT_QT;   // [dk][JT+1]
+  float* sc = kv + ATT_DK_MAX * (ATT_JT + 1);  // [QT][Tpad]
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int i0 = blockIdx.x * ATT_QT;
+  const int len = lens[b];
+  if (i0 >= len) return;
+  const int tid = threadIdx.x;
+  const float* qb = qkv + (size_t)b * bs + (size_t)(h * dk) * ld;
+  const float* kb = qb + (size_t)H * ld;
+  const float* vb = kb + (size_t)H * ld;
+  const float inv_sqrt = 1.f / sqrtf((float)dk);
+  const int nrel = 2 * window + 1;
+
+  for (int e = tid; e < dk * ATT_QT; e += ATT_NT) {
+    const int d = e / ATT_QT, i = e % ATT_QT;
+    qs[d * ATT_QT + i] = (i0 + i) < len ? qb[(size_t)d * ld + i0 + i] : 0.f;
+  }
+  __syncthreads();
+
+  // ---- scores: tile over keys
+  for (int j0 = 0; j0 < len; j0 += ATT_JT) {
+    for (int e = tid; e < dk * ATT_JT; e += ATT_NT) {
+      const int d = e / ATT_JT, j = e % ATT_JT;
+      kv[d * (ATT_JT + 1) + j] = (j0 + j) < len ? kb[(size_t)d * ld + j0 + j] : 0.f;
+    }
+    __syncthreads();
+    for (int e = tid; e < ATT_QT * ATT_JT; e += ATT_NT) {
+      const int i = e / ATT_JT, j = e % ATT_JT;
+      if (j0 + j < len) {
+        float a = 0.f;
+        for (int d = 0; d < dk; ++d) a = fmaf(qs[d * ATT_QT + i], kv[d * (ATT_JT + 1) + j], a);
+        sc[i * Tpad + j0 + j] = a * inv_sqrt;
+      }
+    }
+    __syncthreads();
+  }
+  // ---- relative key logits on the band
+  for (int e = tid; e < ATT_QT * nrel; e += ATT_NT) {
+    const int i = e / nrel, r = e % nrel;
+    const int j = i0 + i + r - window;
+    if ((i0 + i) < len && j >= 0 && j < len) {
+      float a = 0.f;
+      for (int d = 0; d < dk; ++d) a = fmaf(qs[d * ATT_QT + i], emb_k[r * dk + d], a);
+      sc[i * Tpad + j] += a * inv_sqrt;
+    }
+  }
+  __syncthreads();
+  // ---- softmax: one warp per query row
+  {
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int i = warp; i < ATT_QT; i += ATT_NT / 32) {
+      if (i0 + i >= len) continue;
+      float* row = sc + i * Tpad;
+      float mx = -INFINITY;
+      for (int j = lane; j < len; j += 32) mx = fmaxf(mx, row[j]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      float sum = 0.f;
+      for (int j = lane; j < len; j += 32) {
+        const float ev = expf(row[j] - mx);
+        row[j] = ev;
+        sum += ev;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const float inv = 1.f / sum;
+      for (int j = lane; j < len; j += 32) row[j] *= inv;
+    }
+  }
+  __syncthreads();
+  // ---- output: thread owns (d, i) pairs; accumulate over key tiles
+  constexpr int PER = (ATT_DK_MAX * ATT_QT + ATT_NT - 1) / ATT_NT;
+  float oacc[PER];
+#pragma unroll
+  for (int u = 0; u < PER; ++u) oacc[u] = 0.f;
+  for (int j0 = 0; j0 < len; j0 += ATT_JT) {
+    for (int e = tid; e < dk * ATT_JT; e += ATT_NT) {
+      const int d = e / ATT_JT, j = e % ATT_JT;
+      kv[d * (ATT_JT + 1) + j] = (j0 + j) < len ? vb[(size_t)d * ld + j0 + j] : 0.f;
+    }
+    __syncthreads();
+    const int jn = min(ATT_JT, len - j0);
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+      const int e = tid + u * ATT_NT;
+      if (e < dk * ATT_QT) {
+        const int d = e / ATT_QT, i = e % ATT_QT;
+        float a = oacc[u];
+        for (int j = 0; j < jn; ++j) a = fmaf(sc[i * Tpad + j0 + j], kv[d * (ATT_JT + 1) + j], a);
+        oacc[u] = a;
+      }
+    }
+    __syncthreads();
+  }
+  float* ob = out + (size_t)b * out_bs + (size_t)(h * dk) * out_ld;
+#pragma unroll
+  for (int u = 0; u < PER; ++u) {
+    const int e = tid + u * ATT_NT;
+    if (e < dk * ATT_QT) {
+      const int d = e / ATT_QT, i = e % ATT_QT;
+      const int qi = i0 + i;
+      if (qi < len) {
+        float a = oacc[u];
+        for (int r = 0; r < nrel; ++r) {
+          const int j = qi + r - window;
+          if (j >= 0 && j < len) a = fmaf(sc[i * Tpad + j], emb_v[r * dk + d], a);
+        }
+        ob[(size_t)d * out_ld + qi] = a;
+      }
+    }
+  }
+}
+
+void attention_init_attributes() {
+  B2_CUDA(cudaFuncSetAttribute(rel_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+}
+
+void launch_rel_attention(const float* qkv, long long bs, int ld, int H, int n_heads, const float* emb_k,
+                          const float* emb_v, int window, const int* lens, int batch, int Tmax, float* out,
+                          long long out_bs, int out_ld, cudaStream_t s) {
+  const int dk = H / n_heads;
+  B2_CHECK(dk <= ATT_DK_MAX, "attention: head dim too large");
+  const int Tpad = ((Tmax + 31) / 32) * 32 + 1;
+  const size_t smem = sizeof(float) * (ATT_DK_MAX * ATT_QT + ATT_DK_MAX * (ATT_JT + 1) + (size_t)ATT_QT * Tpad);
+  B2_CHECK(smem <= 200 * 1024, "attention: sequence too long for the shared-memory score tile");
+  dim3 grid((Tmax + ATT_QT - 1) / ATT_QT, n_heads, batch);
+  rel_attention_kernel<<<grid, ATT_NT, smem, s>>>(qkv, bs, ld, H, dk, emb_k, emb_v, window, lens, out, out_bs,
+                                                   out_ld, Tpad);
+  B2_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// duration head tail + lengths + alignment   (glow_tts/models.py:49,323-331,356-363; utils.py:99-115)
+//   logw[t] = bias + sum_c w[c]*h[c][t]   (1x1 conv 256->1, masked)
+//   w = exp(logw)*length_scale; w_ceil = ceil(w); cum = inclusive scan; y_len = max(sum,1)//n_sqz*n_sqz
+//   idx[f] = phoneme whose span [cum[i-1], cum[i]) contains frame f  (f < y_len), else -1
+// one block per batch item.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) duration_kernel(const float* __restrict__ h, long long h_bs, int h_ld, int C,
+                                                       const float* __restrict__ pw, const float* __restrict__ pb,
+                                                       const int* __restrict__ lens, int max_tx, float length_scale,
+                                                       int n_sqz, float* __restrict__ logw, int* __restrict__ w_ceil,
+                                                       int* __restrict__ cum, int* __restrict__ y_len) {
+  __shared__ int part[256];
+  const int b = blockIdx.x;
+  const int len = lens[b];
+  const int tid = threadIdx.x;
+  const float* hb = h + (size_t)b * h_bs;
+  // each thread owns a contiguous run of phonemes so the scan is a two-level sum
+  const int per = (max_tx + 255) / 256;
+  const int tbeg = tid * per;
+  int local = 0;
+  for (int u = 0; u < per; ++u) {
+    const int t = tbeg + u;
+    if (t >= max_tx) break;
+    int wc = 0;
+    float lw = 0.f;
+    if (t < len) {
+      float a = 0.f;
+      for (int c = 0; c < C; ++c) a = fmaf(pw[c], hb[(size_t)c * h_ld + t], a);
+      lw = a + pb[0];
+      const float w = expf(lw) * length_scale;
+      wc = (int)ceilf(w);
+    }
+    logw[(size_t)b * max_tx + t] = lw;
+    w_ceil[(size_t)b * max_tx + t] = wc;
+    local += wc;
+  }
+  part[tid] = local;
+  __syncthreads();
+  // exclusive prefix over threads (256 entries: serial per thread is fine, tiny)
+  int before = 0;
+  for (int j = 0; j < tid; ++j) before += part[j];
+  int run = before;
+  for (int u = 0; u < per; ++u) {
+    const int t = tbeg + u;
+    if (t >= max_tx) break;
+    run += w_ceil[(size_t)b * max_tx + t];
+    cum[(size_t)b * max_tx + t] = run;
+  }
+  if (tid == 255) {
+    int total = run;
+    if (total < 1) total = 1;
+    y_len[b] = (total / n_sqz) * n_sqz;
+  }
+}
+
+void launch_duration(const float* h, long long h_bs, int h_ld, int C, const float* pw, const float* pb,
+                     const int* lens, int batch, int max_tx, float length_scale, int n_sqz, float* logw, int* w_ceil,
+                     int* cum, int* y_len, cudaStream_t s) {
+  duration_kernel<<<batch, 256, 0, s>>>(h, h_bs, h_ld, C, pw, pb, lens, max_tx, length_scale, n_sqz, logw, w_ceil,
+                                        cum, y_len);
+  B2_CUDA(cudaGetLastError());
+}
+
+// frame -> phoneme index by binary search over cum (first i with cum[i] > f)
+__global__ void align_index_kernel(const int* __restrict__ cum, const int* __restrict__ lens,
+                                   const int* __restrict__ y_len, int max_tx, int* __restrict__ idx, int idx_ld,
+                                   int* __restrict__ sq_len, int n_sqz) {
+  const int b = blockIdx.y;
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f == 0) sq_len[b] = y_len[b] / n_sqz;
+  if (f >= idx_ld) return;
+  int r = -1;
+  if (f < y_len[b]) {
+    const int* cb = cum + (size_t)b * max_tx;
+    int lo = 0, hi = lens[b] - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (cb[mid] > f) hi = mid;
+      else lo = mid + 1;
+    }
+    r = lo;
+  }
+  idx[(size_t)b * idx_ld + f] = r;
+}
+
+void launch_align_index(const int* cum, const int* lens, const int* y_len, int batch, int max_tx, int* idx, int idx_ld,
+                        int* sq_len, int n_sqz, cudaStream_t s) {
+  if (idx_ld <= 0) idx_ld = 1;
+  dim3 grid((idx_ld + 127) / 128, batch);
+  align_index_kernel<<<grid, 128, 0, s>>>(cum, lens, y_len, max_tx, idx, idx_ld, sq_len, n_sqz);
+  B2_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 + Box-Muller (production noise when no eps is injected)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox_round(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t k0,
+                                             uint32_t k1) {
+  const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+  const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+  c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+}
+__device__ __forceinline__ float philox_normal(unsigned long long seed, unsigned long long ctr) {
+  uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = 0x9E3779B9u, c3 = 0xBB67AE85u;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c0, c1, c2, c3, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  const float u1 = ((float)(c0 >> 8) + 0.5f) * (1.f / 16777216.f);
+  const float u2 = ((float)(c1 >> 8) + 0.5f) * (1.f / 16777216.f);
+  return sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);
+}
+
+// ------------------------------------------------------------------------------------------------
+// expand + noise + squeeze   (glow_tts/models.py:336-348; utils.py:135-147)
+//   z[c][f] = x_m[c][idx[f]] + eps[c][f]*noise_scale   (f < y_len), written squeezed:
+//   zs[(f % n_sqz)*mel + c][f / n_sqz]
+// ------------------------------------------------------------------------------------------------
+__global__ void expand_squeeze_kernel(const float* __restrict__ x_m, long long xm_bs, int xm_ld,
+                                      const int* __restrict__ idx, int idx_ld, const int* __restrict__ y_len,
+                                      const float* __restrict__ eps, long long eps_bs, int eps_ld, float noise_scale,
+                                      unsigned long long seed, int mel, int n_sqz, float* __restrict__ zs,
+                                      long long zs_bs, int zs_ld) {
+  const int b = blockIdx.z, c = blockIdx.y;
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= y_len[b]) return;
+  const int i = idx[(size_t)b * idx_ld + f];
+  float e;
+  if (eps) e = eps[(size_t)b * eps_bs + (size_t)c * eps_ld + f];
+  else e = philox_normal(seed, ((unsigned long long)b << 40) ^ ((unsigned long long)c << 24) ^ (unsigned long long)f);
+  const float v = x_m[(size_t)b * xm_bs + (size_t)c * xm_ld + i] + e * noise_scale;
+  zs[(size_t)b * zs_bs + (size_t)((f % n_sqz) * mel + c) * zs_ld + f / n_sqz] = v;
+}
+
+void launch_expand_squeeze(const float* x_m, long long xm_bs, int xm_ld, const int* idx, int idx_ld, const int* y_len,
+                           const float* eps, long long eps_bs, int eps_ld, float noise_scale, unsigned long long seed,
+                           int mel, int n_sqz, float* zs, long long zs_bs, int zs_ld, int batch, int Tymax,
+                           cudaStream_t s) {
+  if (Tymax <= 0) return;
+  dim3 grid((Tymax + 127) / 128, mel, batch);
+  expand_squeeze_kernel<<<grid, 128, 0, s>>>(x_m, xm_bs, xm_ld, idx, idx_ld, y_len, eps, eps_bs, eps_ld, noise_scale,
+                                             seed, mel, n_sqz, zs, zs_bs, zs_ld);
+  B2_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// unsqueeze (+ optional mel glue)   (glow_tts/utils.py:150-160; larynx/__init__.py:242-249)
+//   mel[c][f] = zs[(f % n_sqz)*mel + c][f / n_sqz] for f < y_len else 0
+//   glued = log(max(10^((denorm(mel))/gain), 1e-5))   (larynx/audio.py:83-108)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float glue_value(float m, const b200tts_glue g) {
+  if (g.signal_norm) {
+    if (g.symmetric_norm) {
+      if (g.clip_norm) m = fminf(fmaxf(m, -g.max_norm), g.max_norm);
+      m = ((m + g.max_norm) * -g.min_level_db / (2.f * g.max_norm)) + g.min_level_db;
+    } else {
+      if (g.clip_norm) m = fminf(fmaxf(m, 0.f), g.max_norm);
+      m = (m * -g.min_level_db / g.max_norm) + g.min_level_db;
+    }
+    m += g.ref_level_db;
+  }
+  if (g.convert_db_to_amp) m = powf(10.f, m / g.spec_gain);
+  if (g.do_dynamic_range_compression) m = logf(fmaxf(m, 1e-5f));
+  return m;
+}
+
+__global__ void unsqueeze_kernel(const float* __restrict__ zs, long long zs_bs, int zs_ld,
+                                 const int* __restrict__ y_len, int mel, int n_sqz, float* __restrict__ out,
+                                 long long out_bs, int out_ld, float* __restrict__ glued, long long gl_bs, int gl_ld,
+                                 const b200tts_glue g, int width) {
+  const int b = blockIdx.z, c = blockIdx.y;
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= width) return;
+  float v = 0.f;
+  const bool valid = f < y_len[b];
+  if (valid) v = zs[(size_t)b * zs_bs + (size_t)((f % n_sqz) * mel + c) * zs_ld + f / n_sqz];
+  if (out && f < out_ld) out[(size_t)b * out_bs + (size_t)c * out_ld + f] = v;
+  if (glued && valid && f < gl_ld) glued[(size_t)b * gl_bs + (size_t)c * gl_ld + f] = glue_value(v, g);
+}
+
+void launch_unsqueeze(const float* zs, long long zs_bs, int zs_ld, const int* y_len, int mel, int n_sqz, float* out,
+                      long long out_bs, int out_ld, float* glued, long long gl_bs, int gl_ld, const b200tts_glue* g,
+                      int batch, int width, cudaStream_t s) {
+  if (width <= 0) return;
+  b200tts_glue gg;
+  if (g) gg = *g;
+  else memset(&gg, 0, sizeof(gg));
+  dim3 grid((width + 127) / 128, mel, batch);
+  unsqueeze_kernel<<<grid, 128, 0, s>>>(zs, zs_bs, zs_ld, y_len, mel, n_sqz, out, out_bs, out_ld, glued, gl_bs, gl_ld,
+                                        gg, width);
+  B2_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv_post: lrelu(0.01) -> Conv1d(C -> 1, k7) -> tanh, + per item |max| (hifi_gan/models.py:198-200)
+// input is the MRF mean of up to three buffers.  One thread per output sample.
+// ------------------------------------------------------------------------------------------------
+constexpr int POST_BT = 256;
+constexpr int POST_KMAX = 7;
+__global__ void __launch_bounds__(POST_BT) conv_post_kernel(const float* __restrict__ x1, const float* __restrict__ x2,
+                                                             const float* __restrict__ x3, long long bs, int ld,
+                                                             float in_div, float slope, const float* __restrict__ w,
+                                                             const float* __restrict__ bias, int C, int K,
+                                                             const int* __restrict__ frames, int len_mul,
+                                                             float* __restrict__ pcm, int pcm_ld,
+                                                             unsigned int* __restrict__ peak_bits) {
+  extern __shared__ float sm[];
+  float* xs = sm;                              // [C][POST_BT + K - 1]
+  float* wsm = sm + C * (POST_BT + POST_KMAX - 1);  // [C][K]
+  const int b = blockIdx.y;
+  const int L = frames[b] * len_mul;
+  const int t0 = blockIdx.x * POST_BT;
+  if (t0 >= L) return;
+  const int W = POST_BT + K - 1, padl = (K - 1) / 2;
+  const float* a1 = x1 + (size_t)b * bs;
+  const float* a2 = x2 ? x2 + (size_t)b * bs : nullptr;
+  const float* a3 = x3 ? x3 + (size_t)b * bs : nullptr;
+  for (int e = threadIdx.x; e < C * W; e += POST_BT) {
+    const int c = e / W, pcol = e % W;
+    const int t = t0 + pcol - padl;
+    float v = 0.f;
+    if (t >= 0 && t < L) {
+      const size_t off = (size_t)c * ld + t;
+      v = a1[off];
+      if (a2) v += a2[off];
+      if (a3) v += a3[off];
+      if (in_div != 1.f) v = v / in_div;
+      v = v > 0.f ? v : v * slope;
+    }
+    xs[c * W + pcol] = v;
+  }
+  for (int e = threadIdx.x; e < C * K; e += POST_BT) wsm[e] = w[e];
+  __syncthreads();
+  const int t = t0 + threadIdx.x;
+  float av = 0.f;
+  if (t < L) {
+    float a = 0.f;
+    for (int c = 0; c < C; ++c)
+      for (int k = 0; k < K; ++k) a = fmaf(wsm[c * K + k], xs[c * W + threadIdx.x + k], a);
+    const float o = tanhf(a + bias[0]);
+    pcm[(size_t)b * pcm_ld + t] = o;
+    av = fabsf(o);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) av = fmaxf(av, __shfl_xor_sync(0xffffffffu, av, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(peak_bits + b, __float_as_uint(av));
+}
+
+void launch_conv_post(const float* x1, const float* x2, const float* x3, long long bs, int ld, float in_div,
+                      float slope, const float* w, const float* bias, int C, int K, const int* frames, int len_mul,
+                      int batch, int Lmax, float* pcm, int pcm_ld, unsigned int* peak_bits, cudaStream_t s) {
+  B2_CHECK(K <= POST_KMAX, "conv_post: kernel too wide");
+  if (Lmax <= 0) return;
+  const size_t smem = sizeof(float) * ((size_t)C * (POST_BT + POST_KMAX - 1) + (size_t)C * K);
+  B2_CHECK(smem <= 48 * 1024, "conv_post: too many channels");
+  dim3 grid((Lmax + POST_BT - 1) / POST_BT, batch);
+  conv_post_kernel<<<grid, POST_BT, smem, s>>>(x1, x2, x3, bs, ld, in_div, slope, w, bias, C, K, frames, len_mul, pcm,
+                                               pcm_ld, peak_bits);
+  B2_CUDA(cudaGetLastError());
+}
+
+// audio_float_to_int16 (larynx/audio.py:118-125): a * (32767 / max(0.01, max|a|)), clip, truncate
+__global__ void pcm_to_i16_kernel(const float* __restrict__ pcm, int pcm_ld, const unsigned int* __restrict__ peak_bits,
+                                  const int* __restrict__ frames, int len_mul, short* __restrict__ out, int out_ld) {
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= out_ld) return;
+  short r = 0;
+  if (t < frames[b] * len_mul) {
+    const float peak = __uint_as_float(peak_bits[b]);
+    const float scale = 32767.0f / fmaxf(0.01f, peak);
+    float v = pcm[(size_t)b * pcm_ld + t] * scale;
+    v = fminf(fmaxf(v, -32767.0f), 32767.0f);
+    r = (short)(int)v;  // truncation toward zero like ndarray.astype("int16")
+  }
+  out[(size_t)b * out_ld + t] = r;
+}
+
+void launch_pcm_to_i16(const float* pcm, int pcm_ld, const unsigned int* peak_bits, const int* frames, int len_mul,
+                       int batch, short* out, int out_ld, cudaStream_t s) {
+  if (out_ld <= 0) return;
+  dim3 grid((out_ld + 255) / 256, batch);
+  pcm_to_i16_kernel<<<grid, 256, 0, s>>>(pcm, pcm_ld, peak_bits, frames, len_mul, out, out_ld);
+  B2_CUDA(cudaGetLastError());
+}
+
+// y[b][c][t] = 0 for t in [lens[b]*len_mul, width)  — keeps padded tails of caller-visible outputs at 0
+__global__ void zero_tail_kernel(float* __restrict__ y, long long bs, int ld, int C, const int* __restrict__ lens,
+                                 int len_mul, int width) {
+  const int b = blockIdx.z, c = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < width && t >= lens[b] * len_mul) y[(size_t)b * bs + (size_t)c * ld + t] = 0.f;
+}
+void launch_zero_tail(float* y, long long bs, int ld, int C, const int* lens, int len_mul, int batch, int width,
+                      cudaStream_t s) {
+  if (width <= 0) return;
+  dim3 grid((width + 255) / 256, C, batch);
+  zero_tail_kernel<<<grid, 256, 0, s>>>(y, bs, ld, C, lens, len_mul, width);
+  B2_CUDA(cudaGetLastError());
+}
+
+}  // namespace b2

@@ -1,0 +1,39 @@
+// kernels.cuh — launch wrappers of the non-conv kernels (definitions in kernels.cu).
+#pragma once
+#include "../../include/b200tts.h"
+#include "common.cuh"
+
+namespace b2 {
+
+int launch_conv1d(const ConvParams& p, int batch, int Lmax, cudaStream_t stream);
+void conv1d_init_attributes();
+void attention_init_attributes();
+
+void launch_embed(const long long* ids, const int* lens, int batch, int max_tx, const float* emb, int n_vocab, int H,
+                  float* x, long long x_bs, int x_ld, cudaStream_t s);
+void launch_layernorm(const float* x, const float* res, const float* gamma, const float* beta, float* y, long long bs,
+                      int ld, int C, const int* lens, int batch, int Lmax, int pre_relu, int post_relu, cudaStream_t s);
+void launch_rel_attention(const float* qkv, long long bs, int ld, int H, int n_heads, const float* emb_k,
+                          const float* emb_v, int window, const int* lens, int batch, int Tmax, float* out,
+                          long long out_bs, int out_ld, cudaStream_t s);
+void launch_duration(const float* h, long long h_bs, int h_ld, int C, const float* pw, const float* pb,
+                     const int* lens, int batch, int max_tx, float length_scale, int n_sqz, float* logw, int* w_ceil,
+                     int* cum, int* y_len, cudaStream_t s);
+void launch_align_index(const int* cum, const int* lens, const int* y_len, int batch, int max_tx, int* idx, int idx_ld,
+                        int* sq_len, int n_sqz, cudaStream_t s);
+void launch_expand_squeeze(const float* x_m, long long xm_bs, int xm_ld, const int* idx, int idx_ld, const int* y_len,
+                           const float* eps, long long eps_bs, int eps_ld, float noise_scale, unsigned long long seed,
+                           int mel, int n_sqz, float* zs, long long zs_bs, int zs_ld, int batch, int Tymax,
+                           cudaStream_t s);
+void launch_unsqueeze(const float* zs, long long zs_bs, int zs_ld, const int* y_len, int mel, int n_sqz, float* out,
+                      long long out_bs, int out_ld, float* glued, long long gl_bs, int gl_ld, const b200tts_glue* g,
+                      int batch, int width, cudaStream_t s);
+void launch_conv_post(const float* x1, const float* x2, const float* x3, long long bs, int ld, float in_div,
+                      float slope, const float* w, const float* bias, int C, int K, const int* frames, int len_mul,
+                      int batch, int Lmax, float* pcm, int pcm_ld, unsigned int* peak_bits, cudaStream_t s);
+void launch_pcm_to_i16(const float* pcm, int pcm_ld, const unsigned int* peak_bits, const int* frames, int len_mul,
+                       int batch, short* out, int out_ld, cudaStream_t s);
+void launch_zero_tail(float* y, long long bs, int ld, int C, const int* lens, int len_mul, int batch, int width,
+                      cudaStream_t s);
+
+}  // namespace b2

@@ -1,0 +1,177 @@
+"""Thin object layer over the C ABI: device-resident models + per-thread call contexts.
+
+Nothing here computes: numpy/torch objects are only containers whose addresses are handed to
+libb200tts.so (host or device pointers are both accepted by the library).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import Glue, check, ptr
+
+
+class Call:
+    """b200tts_call: one CUDA stream + workspaces.  Not thread-safe — use one per host thread."""
+
+    def __init__(self, device: int = 0):
+        self.device = int(device)
+        self._h = C.c_void_p()
+        check(_lib.load().b200tts_call_create(self.device, C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            _lib.load().b200tts_call_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):  # best effort
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    @property
+    def last_ms(self) -> float:
+        v = C.c_float()
+        check(_lib.load().b200tts_call_last_ms(self._h, C.byref(v)))
+        return v.value
+
+    @property
+    def launches(self) -> int:
+        v = C.c_int64()
+        check(_lib.load().b200tts_call_launches(self._h, C.byref(v)))
+        return v.value
+
+    @property
+    def stream(self) -> int:
+        v = C.c_void_p()
+        check(_lib.load().b200tts_call_stream(self._h, C.byref(v)))
+        return v.value or 0
+
+    def set_debug(self, on: bool):
+        check(_lib.load().b200tts_call_set_debug(self._h, int(on)))
+
+
+class _CallPool:
+    """One Call per (host thread, device): `_sentence_task` runs on ThreadPoolExecutor workers against
+    one shared model object (larynx/__init__.py:146-157), so the model must be re-entrant."""
+
+    def __init__(self):
+        self._tls = threading.local()
+
+    def get(self, device: int) -> Call:
+        d: Dict[int, Call] = getattr(self._tls, "calls", None)
+        if d is None:
+            d = {}
+            self._tls.calls = d
+        if device not in d:
+            d[device] = Call(device)
+        return d[device]
+
+
+CALLS = _CallPool()
+
+
+def _as_blob(blob):
+    if isinstance(blob, np.ndarray):
+        assert blob.dtype == np.uint8 and blob.flags["C_CONTIGUOUS"]
+        return blob.ctypes.data, blob.nbytes
+    if hasattr(blob, "data_ptr"):  # torch uint8 tensor, host or device (e.g. after an NCCL broadcast)
+        assert blob.is_contiguous()
+        return blob.data_ptr(), blob.numel() * blob.element_size()
+    raise TypeError(type(blob))
+
+
+class GlowModel:
+    """b200tts_glow: GlowTTS weights resident on one device (immutable, shareable across threads)."""
+
+    def __init__(self, blob, device: int = 0):
+        self.device = int(device)
+        self._h = C.c_void_p()
+        addr, n = _as_blob(blob)
+        check(_lib.load().b200tts_glow_create(addr, n, self.device, C.byref(self._h)))
+        a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
+        check(_lib.load().b200tts_glow_info(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        self.num_symbols, self.mel_channels, self.n_sqz = a.value, b.value, c.value
+
+    def close(self):
+        if self._h:
+            _lib.load().b200tts_glow_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def encode(self, call: Call, ids, x_len, batch: int, max_tx: int, length_scale: float = 1.0) -> np.ndarray:
+        """Phase A.  ids [batch, max_tx] int64, x_len [batch] int32 (numpy or device tensors)."""
+        y_len = np.zeros(batch, dtype=np.int32)
+        check(_lib.load().b200tts_glow_encode(self._h, call._h, ptr(ids), ptr(x_len), batch, max_tx, float(length_scale), ptr(y_len)))
+        return y_len
+
+    def decode(self, call: Call, mel_out, mel_ld: int, noise_scale: float = 0.667, eps=None, eps_ld: int = 0, seed: int = 0):
+        check(_lib.load().b200tts_glow_decode(self._h, call._h, float(noise_scale), ptr(eps), int(eps_ld), int(seed), ptr(mel_out), int(mel_ld)))
+
+    def alignment(self, call: Call, batch: int, max_tx: int, ty_max: int):
+        logw = np.zeros((batch, max_tx), dtype=np.float32)
+        w_ceil = np.zeros((batch, max_tx), dtype=np.int32)
+        idx = np.full((batch, max(ty_max, 1)), -1, dtype=np.int32)
+        check(_lib.load().b200tts_glow_alignment(self._h, call._h, ptr(logw), ptr(w_ceil), ptr(idx), idx.shape[1]))
+        return logw, w_ceil, idx[:, :ty_max]
+
+    def flow_tap(self, call: Call, blk: int, batch: int, tq: int) -> np.ndarray:
+        out = np.zeros((batch, self.mel_channels * self.n_sqz, max(tq, 1)), dtype=np.float32)
+        check(_lib.load().b200tts_glow_flow_tap(self._h, call._h, blk, ptr(out), out.shape[2]))
+        return out[:, :, :tq]
+
+
+class HifiGanModel:
+    """b200tts_hifigan: HiFi-GAN generator weights resident on one device."""
+
+    def __init__(self, blob, device: int = 0):
+        self.device = int(device)
+        self._h = C.c_void_p()
+        addr, n = _as_blob(blob)
+        check(_lib.load().b200tts_hifigan_create(addr, n, self.device, C.byref(self._h)))
+        a, b = C.c_int32(), C.c_int32()
+        check(_lib.load().b200tts_hifigan_info(self._h, C.byref(a), C.byref(b)))
+        self.mel_channels, self.hop = a.value, b.value
+
+    def close(self):
+        if self._h:
+            _lib.load().b200tts_hifigan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def infer(self, call: Call, mel, frames, batch: int, mel_ld: int, pcm_f32=None, pcm_i16=None, pcm_ld: int = 0):
+        check(_lib.load().b200tts_hifigan_infer(self._h, call._h, ptr(mel), ptr(frames), batch, int(mel_ld), ptr(pcm_f32), ptr(pcm_i16), int(pcm_ld)))
+
+
+def tts_finish(glow: GlowModel, voc: HifiGanModel, call: Call, glue: Glue, noise_scale: float, eps, eps_ld: int, seed: int,
+               mel_out, mel_ld: int, pcm_f32, pcm_i16, pcm_ld: int):
+    check(_lib.load().b200tts_tts_finish(glow._h, voc._h, call._h, C.byref(glue), float(noise_scale), ptr(eps), int(eps_ld), int(seed),
+                                         ptr(mel_out), int(mel_ld), ptr(pcm_f32), ptr(pcm_i16), int(pcm_ld)))
+
+
+def pad_ids(id_rows: Sequence[np.ndarray]):
+    """Ragged list of id arrays -> (ids [B, max_tx] int64 zero padded, x_len [B] int32)."""
+    b = len(id_rows)
+    max_tx = max((len(r) for r in id_rows), default=0)
+    ids = np.zeros((b, max(max_tx, 1)), dtype=np.int64)
+    x_len = np.zeros(b, dtype=np.int32)
+    for i, r in enumerate(id_rows):
+        r = np.asarray(r, dtype=np.int64).reshape(-1)
+        ids[i, : len(r)] = r
+        x_len[i] = len(r)
+    return ids, x_len

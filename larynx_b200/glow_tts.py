@@ -1,0 +1,84 @@
+"""Drop-in for `larynx.glow_tts.GlowTextToSpeech` (larynx/glow_tts.py:29-170) on libb200tts.
+
+Same constructor (a TextToSpeechModelConfig whose model_path holds `generator.pth` + `config.json`),
+same `phonemes_to_mels(phoneme_ids, settings)` contract: int64 ids [T_x] in, float32 mel
+[1, 80, T_y] numpy array out (what the ONNX backend returns, larynx/glow_tts.py:161-170), same
+settings keys (`noise_scale` 0.667, `length_scale` 1.0; larynx/glow_tts.py:104-121).
+Extra, optional settings: `eps` (injected N(0,1) noise [80, >=T_y], for parity tests) and `seed`.
+"""
+from __future__ import annotations
+
+import itertools
+import json
+import logging
+import os
+import typing
+from pathlib import Path
+
+import numpy as np
+
+from . import pack
+from .constants import ARRAY_OR_TENSOR, SettingsType, TextToSpeechModel, TextToSpeechModelConfig
+from .engine import CALLS, GlowModel
+
+_LOGGER = logging.getLogger("larynx_b200.glow_tts")
+
+
+def default_device() -> int:
+    return int(os.environ.get("B200TTS_DEVICE", "0"))
+
+
+class GlowTextToSpeech(TextToSpeechModel):
+    def __init__(self, config: TextToSpeechModelConfig, device: typing.Optional[int] = None, blob=None,
+                 model_config: typing.Optional[dict] = None):
+        super().__init__(config)
+        self.device = default_device() if device is None else int(device)
+        model_path = Path(config.model_path) if config is not None else None
+        if model_config is None:
+            with open(model_path / "config.json", "r", encoding="utf-8") as f:
+                model_config = json.load(f)
+        self.config = model_config
+        if blob is None:
+            pytorch_path = model_path / "generator.pth"
+            if not pytorch_path.is_file():
+                raise FileNotFoundError(
+                    f"{pytorch_path} not found: larynx_b200 reads the PyTorch checkpoint of a voice "
+                    "(generator.onnx alone cannot be read without the onnx package)"
+                )
+            _LOGGER.debug("Packing GlowTTS weights from %s", pytorch_path)
+            blob = pack.pack_glow(pack.load_state_dict(pytorch_path, "model"), model_config)
+        self.model = GlowModel(blob, self.device)
+        self.noise_scale = 0.667
+        self.length_scale = 1.0
+        self._seed = itertools.count(1)
+
+    # ---------------------------------------------------------------------------------------
+    def phonemes_to_mels(self, phoneme_ids: np.ndarray, settings: typing.Optional[SettingsType] = None) -> ARRAY_OR_TENSOR:
+        """Convert phoneme ids to mel spectrograms (float32 [1, mel, T_y])."""
+        noise_scale, length_scale = self.noise_scale, self.length_scale
+        eps = None
+        seed = None
+        if settings:
+            noise_scale = float(settings.get("noise_scale", noise_scale))
+            length_scale = float(settings.get("length_scale", length_scale))
+            if settings.get("speaker_id") is not None:
+                raise ValueError("multi-speaker voices are not supported by larynx_b200")
+            eps = settings.get("eps")
+            seed = settings.get("seed")
+        ids = np.ascontiguousarray(np.asarray(phoneme_ids, dtype=np.int64).reshape(1, -1))
+        if ids.shape[1] == 0:
+            return np.zeros((1, self.model.mel_channels, 0), dtype=np.float32)
+        x_len = np.array([ids.shape[1]], dtype=np.int32)
+        call = CALLS.get(self.device)
+        y_len = self.model.encode(call, ids, x_len, 1, ids.shape[1], length_scale)
+        t_y = int(y_len[0])
+        mel = np.zeros((1, self.model.mel_channels, t_y), dtype=np.float32)
+        if t_y == 0:
+            return mel
+        eps_ld = 0
+        if eps is not None:
+            eps = np.ascontiguousarray(np.asarray(eps, dtype=np.float32)[:, :t_y])
+            assert eps.shape == (self.model.mel_channels, t_y), "eps must be [mel, >= T_y]"
+            eps_ld = t_y
+        self.model.decode(call, mel, t_y, noise_scale, eps, eps_ld, int(seed) if seed is not None else next(self._seed))
+        return mel

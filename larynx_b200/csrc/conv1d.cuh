@@ -30,7 +30,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
 constexpr int CONV_CK = 8;        // input channels per smem stage
-constexpr int CONV_HALO_MAX = 64; // (K-1)*dil must be <= this
+constexpr int CONV_HALO_MAX = 80; // (K-1)*dil must be <= this (vctk_small: k7, dil 12 -> 72)
 
 template <int BM, int BN, int TM, int TN>
 struct ConvCfg {

@@ -1,0 +1,114 @@
+"""TEST INFRASTRUCTURE — generates tests/golden/*.npz by running the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference):  python -m oracle.make_golden
+
+What is executed: the reference's own loaders and modules — glow_tts/checkpoint.py:26-68,
+hifi_gan/checkpoint.py:36-70, FlowGenerator.forward (glow_tts/models.py:308-354) with
+decoder.store_inverse() (larynx/glow_tts.py:94), Generator.forward (hifi_gan/models.py:186-202)
+after remove_weight_norm() (larynx/hifi_gan.py:100), AudioSettings glue (larynx/audio.py:58-108)
+and audio_float_to_int16 (larynx/audio.py:118-125) — on the synthetic reference-format voices of
+larynx_b200/synth.py (seeds below).  Weights are regenerated bit-identically from the seeds on any
+machine, so only inputs and outputs are committed.
+"""
+from __future__ import annotations
+
+import sys
+import tempfile
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+from larynx_b200 import synth  # noqa: E402
+from oracle import ref_harness  # noqa: E402
+
+GLOW_SEED, HIFI_SEED, EPS_SEED = 1234, 4321, 1234
+NOISE_SCALE, LENGTH_SCALE = 0.667, 1.0
+
+FIXTURE_28 = "3 8 4 14 3 35 3 26 4 34 22 3 1 3 19 4 32 23 3 35 19 3 4 37 16 20 3 2"  # be_a_voice_not_an_echo
+
+
+def run_case(glow, gen, ids, audio_settings, taps_at=()):
+    import larynx.audio as laudio  # the reference's own glue
+
+    eps = synth.seeded_eps(4096, seed=EPS_SEED)
+    captured = {}
+    hooks = []
+    for blk in taps_at:
+        # flows = [ActNorm_0, InvConv_0, Coupling_0, ...]; in reverse the ActNorm of block `blk` runs last
+        mod = glow.decoder.flows[3 * blk]
+        hooks.append(mod.register_forward_hook(lambda m, i, o, blk=blk: captured.__setitem__(blk, o[0].detach().clone())))
+    r = ref_harness.run_reference_glow(glow, ids, NOISE_SCALE, LENGTH_SCALE, eps)
+    for h in hooks:
+        h.remove()
+    mel = r["mel"].numpy()
+    attn = r["attn"].squeeze(1)[0].numpy()  # [t_x, t_y] one-hot
+    idx = attn.argmax(0).astype(np.int32)
+    assert np.all(attn.sum(0) == 1.0)
+    logw = r["logw"].numpy().reshape(-1)
+    w = np.exp(logw)
+    aset = laudio.AudioSettings(**audio_settings)
+    m2 = mel
+    if aset.signal_norm:
+        m2 = aset.denormalize(m2)
+    if aset.convert_db_to_amp:
+        m2 = aset.db_to_amp(m2)
+    if aset.do_dynamic_range_compression:
+        m2 = aset.dynamic_range_compression(m2)
+    m2 = m2.astype(np.float32)
+    with torch.no_grad():
+        pcm = gen(torch.from_numpy(m2)).squeeze(0).numpy()
+    audio = laudio.audio_float_to_int16(pcm).squeeze()
+    out = {
+        "ids": np.asarray(ids, dtype=np.int64),
+        "mel": mel[0],
+        "mel_glued": m2[0],
+        "logw": logw.astype(np.float32),
+        "w_ceil": np.ceil(w * LENGTH_SCALE).astype(np.int32),
+        "idx": idx,
+        "pcm": pcm.reshape(-1).astype(np.float32),
+        "audio": audio.astype(np.int16),
+        "ceil_margin": np.array(np.abs(w - np.round(w)).min(), dtype=np.float32),
+    }
+    for blk, t in captured.items():
+        out[f"flow{blk}"] = t[0].numpy()
+    return out
+
+
+def main():
+    assert ref_harness.available(), "/root/reference is required to regenerate the golden vectors"
+    tmp = Path(tempfile.mkdtemp())
+    synth.write_glow_voice(tmp / "glow", 46, GLOW_SEED)
+    synth.write_hifigan_voice(tmp / "hifi", "universal_large", HIFI_SEED)
+    glow, gen = ref_harness.load_reference_models(tmp / "glow", tmp / "hifi")
+    audio_settings = synth.glow_config(46)["audio"]
+    outdir = ROOT / "tests" / "golden"
+    outdir.mkdir(parents=True, exist_ok=True)
+    meta = dict(glow_seed=GLOW_SEED, hifi_seed=HIFI_SEED, eps_seed=EPS_SEED, noise_scale=NOISE_SCALE, length_scale=LENGTH_SCALE)
+
+    a = run_case(glow, gen, np.array([int(x) for x in FIXTURE_28.split()]), audio_settings, taps_at=(11, 6, 0))
+    np.savez_compressed(outdir / "ljspeech_fixture28.npz", **a, **{k: np.array(v) for k, v in meta.items()})
+    print("fixture28: T_y", a["mel"].shape[1], "ceil margin", float(a["ceil_margin"]))
+
+    b = run_case(glow, gen, synth.bench_ids(128), audio_settings)
+    b["pcm"] = b["pcm"][::16].copy()  # keep the fixture small: every 16th float sample + all int16 samples
+    np.savez_compressed(outdir / "bench128.npz", **b, **{k: np.array(v) for k, v in meta.items()})
+    print("bench128: T_y", b["mel"].shape[1], "ceil margin", float(b["ceil_margin"]))
+
+    # second vocoder family (ResBlock2, 3 upsamplers): vctk_small on the fixture-28 mel
+    synth.write_hifigan_voice(tmp / "hifi_small", "vctk_small", HIFI_SEED)
+    synth.write_hifigan_voice(tmp / "hifi_medium", "vctk_medium", HIFI_SEED)
+    for name in ("vctk_small", "vctk_medium"):
+        _, g2 = ref_harness.load_reference_models(tmp / "glow", tmp / ("hifi_small" if name == "vctk_small" else "hifi_medium"))
+        with torch.no_grad():
+            pcm = g2(torch.from_numpy(a["mel_glued"][None])).reshape(-1).numpy()
+        np.savez_compressed(outdir / f"{name}_fixture28.npz", mel_glued=a["mel_glued"], pcm=pcm.astype(np.float32),
+                            hifi_seed=np.array(HIFI_SEED))
+        print(name, "pcm std", float(pcm.std()), "absmax", float(np.abs(pcm).max()))
+
+
+if __name__ == "__main__":
+    main()

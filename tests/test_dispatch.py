@@ -1,0 +1,65 @@
+"""Host logic of the multi-GPU path on CPU: gloo, world_size 2 (no GPU needed)."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from larynx_b200 import dispatch
+
+
+def test_sharding_is_a_partition():
+    for n, w in ((10, 3), (7, 8), (0, 2), (16, 4)):
+        seen = sorted(i for r in range(w) for i in dispatch.shard_round_robin(n, r, w))
+        assert seen == list(range(n))
+    costs = [5, 1, 9, 3, 3, 7, 2, 8]
+    parts = dispatch.shard_by_cost(costs, 3)
+    assert sorted(i for p in parts for i in p) == list(range(len(costs)))
+    loads = [sum(costs[i] for i in p) for p in parts]
+    assert max(loads) - min(loads) <= max(costs)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        calls = []
+
+        def make():
+            calls.append(1)
+            return (np.arange(100_003) % 251).astype(np.uint8)
+
+        blob = dispatch.broadcast_blob(make if rank == 0 else None)
+        assert blob.dtype == torch.uint8 and blob.numel() == 100_003
+        assert int(blob.to(torch.int64).sum()) == int(((np.arange(100_003) % 251)).sum())
+        assert len(calls) == (1 if rank == 0 else 0), "only the source rank packs the voice"
+        mine = dispatch.shard_round_robin(9, rank, world)
+        local = {i: ("utt%d" % i, rank) for i in mine}
+        ordered = dispatch.gather_in_order(local, 9)
+        assert [o[0] for o in ordered] == ["utt%d" % i for i in range(9)]
+        assert [o[1] for o in ordered] == [i % world for i in range(9)]
+        out.put((rank, "ok"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_broadcast_and_gather_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    [p.join(120) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    got = sorted(q.get(timeout=5) for _ in range(2))
+    assert got == [(0, "ok"), (1, "ok")]

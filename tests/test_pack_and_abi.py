@@ -1,0 +1,123 @@
+"""Host-side logic: weight packer layouts, blob format, and the C-ABI surface (no GPU needed)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from larynx_b200 import _lib, pack, synth
+from tests import common
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_fold_weight_norm_matches_torch():
+    torch.manual_seed(0)
+    conv = torch.nn.utils.weight_norm(torch.nn.Conv1d(6, 10, 5))
+    conv.weight_g.data.mul_(torch.rand(10, 1, 1) + 0.5)
+    sd = {k: v.detach().numpy() for k, v in conv.state_dict().items()}
+    sd = {"c." + k: v for k, v in sd.items()}
+    w = pack.fold_weight_norm(sd, "c")
+    x = torch.randn(1, 6, 20)
+    assert np.abs(conv(x).detach().numpy() - F.conv1d(x, torch.from_numpy(w), conv.bias).detach().numpy()).max() < 1e-5
+    # ConvTranspose1d: weight_norm dim=0 is the *input* channel axis
+    ct = torch.nn.utils.weight_norm(torch.nn.ConvTranspose1d(6, 4, 8, 4, padding=2))
+    sd = {"t." + k: v.detach().numpy() for k, v in ct.state_dict().items()}
+    assert sd["t.weight_g"].shape == (6, 1, 1)
+    w = pack.fold_weight_norm(sd, "t")
+    assert np.abs(ct(x).detach().numpy() - F.conv_transpose1d(x, torch.from_numpy(w), ct.bias, stride=4, padding=2).detach().numpy()).max() < 1e-5
+
+
+def test_polyphase_equals_conv_transpose():
+    rs = np.random.RandomState(0)
+    for u in (8, 2, 4):
+        k = 2 * u
+        cin, cout, L = 5, 3, 17
+        w = rs.standard_normal((cin, cout, k)).astype(np.float32)
+        x = rs.standard_normal((cin, L)).astype(np.float32)
+        ref = F.conv_transpose1d(torch.from_numpy(x)[None], torch.from_numpy(w), stride=u, padding=(k - u) // 2)[0].numpy()
+        pw = pack.polyphase(w, u, k)  # [u][cin][2][cout]
+        pad = (k - u) // 2
+        out = np.zeros((cout, L * u), dtype=np.float64)
+        xp = np.pad(x, ((0, 0), (2, 2)))
+        for r in range(u):
+            q = (r + pad) // u
+            for t in range(L):
+                a = xp[:, t + q - 1 + 2] @ pw[r, :, 0, :] + xp[:, t + q + 2] @ pw[r, :, 1, :]
+                out[:, t * u + r] = a
+        assert ref.shape == out.shape
+        assert np.abs(ref - out).max() < 1e-4
+
+
+def test_interleave_and_conv_layout():
+    w = np.arange(8 * 3 * 2, dtype=np.float32).reshape(8, 3, 2)
+    b = np.arange(8, dtype=np.float32)
+    wi, bi = pack.interleave_halves(w, b)
+    assert list(bi) == [0, 4, 1, 5, 2, 6, 3, 7]
+    assert np.array_equal(wi[1], w[4])
+    cl = pack.conv_layout(w)
+    assert cl.shape == (3, 2, 8) and cl[1, 0, 5] == w[5, 1, 0]
+
+
+def test_blob_roundtrip_table():
+    cfg = common.glow_cfg()
+    blob = pack.pack_glow(common.glow_sd_np(), cfg)
+    magic, ver, kind, n, ncfg, *rest = pack._HEADER.unpack_from(blob.tobytes()[: pack._HEADER.size])
+    assert magic == pack.MAGIC and ver == 1 and kind == pack.KIND_GLOW and ncfg == 16
+    assert rest[-1] == blob.nbytes
+    assert rest[0] == 46 and rest[1] == 192 and rest[8] == 80
+    names = {}
+    p = pack._HEADER.size
+    raw = blob.tobytes()
+    for _ in range(n):
+        name, off, numel, dt, _r = pack._ENTRY.unpack_from(raw, p)
+        names[name.rstrip(b"\0").decode()] = (off, numel)
+        assert off % 256 == 0 and off + numel * 4 <= blob.nbytes
+        p += pack._ENTRY.size
+    off, numel = names["flow3.an_scale"]
+    got = blob[off : off + numel * 4].view(np.float32)
+    assert np.allclose(got, np.exp(-common.glow_sd_np()["decoder.flows.9.logs"].reshape(-1)))
+    off, numel = names["flow0.inv"]
+    winv = blob[off : off + 64].view(np.float32).reshape(4, 4)
+    assert np.abs(winv @ common.glow_sd_np()["decoder.flows.1.weight"] - np.eye(4)).max() < 1e-5
+    # 28.57 M parameters -> ~114 MB
+    assert 110e6 < blob.nbytes < 120e6
+
+
+def test_synth_param_counts():
+    # GlowTTS 28,569,745 parameters counting weight_v only for the weight-normed convs
+    n_glow = sum(v.size for k, v in common.glow_sd_np().items() if not k.endswith("weight_g"))
+    assert abs(n_glow - 28_569_745) < 4096
+    sd = common.hifi_sd_np()
+    n_folded = sum(v.size for k, v in sd.items() if not k.endswith("weight_g"))
+    assert n_folded == 13_926_017
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "b200tts.h")).read()
+    declared = set(re.findall(r"\b(b200tts_[a-z0-9_]+)\s*\(", header))
+    declared -= {"b200tts_call_set_debug(call,1)"}
+    assert len(declared) >= 20
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), f"libb200tts.so does not export {name}"
+    assert set(_lib.EXPORTED_SYMBOLS) == declared
+    assert lib.b200tts_version() == 1
+
+
+def test_fails_loudly_without_device_or_with_bad_blob():
+    lib = _lib.load()
+    try:
+        ngpu = torch.cuda.device_count()
+    except Exception:  # noqa: BLE001
+        ngpu = 0
+    h = ctypes.c_void_p()
+    junk = np.zeros(4096, dtype=np.uint8)
+    rc = lib.b200tts_glow_create(junk.ctypes.data, junk.nbytes, 0, ctypes.byref(h))
+    assert rc != 0
+    msg = lib.b200tts_last_error().decode()
+    assert msg  # either "bad blob magic" (GPU present) or a CUDA error (no device): never a silent fallback
+    if ngpu == 0:
+        assert "CUDA" in msg

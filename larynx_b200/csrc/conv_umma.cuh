@@ -36,9 +36,19 @@ struct UmmaCfg {
   static size_t a_stage_bytes(int nsplit) { return (size_t)nsplit * UM_KCH * RA * 16; }
   static size_t w_stage_bytes(int nsplit, int NT) { return (size_t)nsplit * UM_KCH * NT * 16; }
   static size_t smem_bytes(int nsplit, int NT) {
-    return UM_ASTAGES * a_stage_bytes(nsplit) + UM_WSTAGES * w_stage_bytes(nsplit, NT) + 256;
+    return UM_ASTAGES * a_stage_bytes(nsplit) + UM_WSTAGES * w_stage_bytes(nsplit, NT) + 128 + 4 * (256 + 16 + 2 * 256);
   }
 };
+
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define UM_TRACE(slot)                                                                         \
+  do {                                                                                         \
+    if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.dbg[slot] = gtimer(); \
+  } while (0)
 
 __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
@@ -64,6 +74,7 @@ __global__ void __launch_bounds__(UM_NT_THREADS, MT == 1 ? 2 : 1) conv_umma_kern
   uint64_t* w_empty = bars + 8;                 // [UM_WSTAGES]
   uint64_t* acc_full = bars + 12;               // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  float* s_bias = reinterpret_cast<float*>(bars + 16);  // [NT] bias of this N tile (+ [16+2*half] coupling constants)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.z;
@@ -80,6 +91,7 @@ __global__ void __launch_bounds__(UM_NT_THREADS, MT == 1 ? 2 : 1) conv_umma_kern
   constexpr int NACC = NSPLIT;
   while (tmem_cols < (uint32_t)(NACC * MT * NT)) tmem_cols <<= 1;
 
+  if (tid == 0) UM_TRACE(0);
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&a_full[i], UM_NPROD / 32);
@@ -93,10 +105,23 @@ __global__ void __launch_bounds__(UM_NT_THREADS, MT == 1 ? 2 : 1) conv_umma_kern
     fence_barrier_init();
   }
   if (warp == 8) tmem_alloc(tmem_slot, tmem_cols);
+  // epilogue constants -> smem (global loads in the epilogue would serialise on L2 latency)
+  for (int i = tid; i < NT; i += UM_NT_THREADS) s_bias[i] = (n0 + i) < p.Cout ? p.bias[n0 + i] : 0.f;
+  float* s_inv = s_bias + 256;        // [16]
+  float* s_anb = s_inv + 16;          // [2*half] ActNorm bias
+  float* s_ans = s_anb + 256;         // [2*half] ActNorm exp(-logs)
+  if (p.epi == EPI_COUPLING) {
+    if (tid < 16) s_inv[tid] = p.inv_w[tid];
+    for (int i = tid; i < 2 * p.half; i += UM_NT_THREADS) {
+      s_anb[i] = p.an_bias[i];
+      s_ans[i] = p.an_scale[i];
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  if (tid == 0) UM_TRACE(1);
 
   if (warp == 9) {
     // ===================== weight producer =====================
@@ -121,6 +146,7 @@ __global__ void __launch_bounds__(UM_NT_THREADS, MT == 1 ? 2 : 1) conv_umma_kern
         const int as = c & 1;
         mbar_wait(&a_full[as], (c >> 1) & 1);
         tc_fence_after();
+        if (c == 0) UM_TRACE(3);
         for (int k = 0; k < K; ++k, ++n) {
           const int s = n % UM_WSTAGES;
           mbar_wait(&w_full[s], (n / UM_WSTAGES) & 1);
@@ -155,6 +181,7 @@ __global__ void __launch_bounds__(UM_NT_THREADS, MT == 1 ? 2 : 1) conv_umma_kern
         mma_commit(&a_empty[as]);   // frees the activation stage
       }
       mma_commit(acc_full);
+      UM_TRACE(4);
     }
   } else {
     // ===================== A producers (warps 0..7) =====================
@@ -229,11 +256,14 @@ __global__ void __launch_bounds__(UM_NT_THREADS, MT == 1 ? 2 : 1) conv_umma_kern
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&a_full[as]);
+      if (tid == 0 && c == 0) UM_TRACE(2);
+      if (tid == 0 && c == nch - 1) UM_TRACE(5);
     }
 
     // ===================== epilogue (same warps) =====================
     mbar_wait(acc_full, 0);
     tc_fence_after();
+    if (tid == 0) UM_TRACE(6);
     const int quad = warp & 3;
     const int grp = warp >> 2;  // MT == 2: the M tile; MT == 1: which half of the N columns
     const int mt = MT == 2 ? grp : 0;
@@ -278,7 +308,7 @@ __global__ void __launch_bounds__(UM_NT_THREADS, MT == 1 ? 2 : 1) conv_umma_kern
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           if (j < jmax) {
-            float v = acc[j] + __ldg(p.bias + nb + j);
+            float v = acc[j] + s_bias[g * 32 + j];
             if (p.act == ACT_RELU) v = fmaxf(v, 0.f);
             else if (p.act == ACT_TANH) v = tanhf(v);
             yb[(size_t)(nb + j) * p.y_ld] = v + rv[j];
@@ -289,7 +319,7 @@ __global__ void __launch_bounds__(UM_NT_THREADS, MT == 1 ? 2 : 1) conv_umma_kern
         float* __restrict__ yb = p.y + (size_t)b * p.y_bs;
         const int u = p.pix;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j] += j < jmax ? __ldg(p.bias + nb + j) : 0.f;
+        for (int j = 0; j < 32; ++j) acc[j] += j < jmax ? s_bias[g * 32 + j] : 0.f;
         if (u == 8 && jmax == 32) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -320,8 +350,8 @@ __global__ void __launch_bounds__(UM_NT_THREADS, MT == 1 ? 2 : 1) conv_umma_kern
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
           if (j < jmax) {
-            const float a = acc[j] + __ldg(p.bias + nb + j);
-            const float gt = acc[j + 1] + __ldg(p.bias + nb + j + 1);
+            const float a = acc[j] + s_bias[g * 32 + j];
+            const float gt = acc[j + 1] + s_bias[g * 32 + j + 1];
             yb[(size_t)((nb + j) >> 1) * p.y_ld] = tanhf(a) * (1.f / (1.f + expf(-gt)));
           }
         }
@@ -342,7 +372,7 @@ __global__ void __launch_bounds__(UM_NT_THREADS, MT == 1 ? 2 : 1) conv_umma_kern
         for (int j = 0; j < 32; ++j) {
           const int co = nb + j;
           if (j < jmax) {
-            const float v = old[j] + (acc[j] + __ldg(p.bias + co));
+            const float v = old[j] + (acc[j] + s_bias[g * 32 + j]);
             if (co < p.split) yb[(size_t)co * p.y_ld] = v;
             else ab[(size_t)(co - p.split) * p.aux_ld] = v;
           }
@@ -361,7 +391,7 @@ __global__ void __launch_bounds__(UM_NT_THREADS, MT == 1 ? 2 : 1) conv_umma_kern
         }
         float wi[16];
 #pragma unroll
-        for (int o = 0; o < 16; ++o) wi[o] = __ldg(p.inv_w + o);
+        for (int o = 0; o < 16; ++o) wi[o] = s_inv[o];
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           if (j < jmax) {
@@ -371,24 +401,26 @@ __global__ void __launch_bounds__(UM_NT_THREADS, MT == 1 ? 2 : 1) conv_umma_kern
             float vin[4];
             vin[0] = xin[j + 0];
             vin[1] = xin[j + 1];
-            vin[2] = (xin[j + 2] - (acc[j] + __ldg(p.bias + co))) * expf(-(acc[j + 1] + __ldg(p.bias + co + 1)));
-            vin[3] = (xin[j + 3] - (acc[j + 2] + __ldg(p.bias + co + 2))) * expf(-(acc[j + 3] + __ldg(p.bias + co + 3)));
+            vin[2] = (xin[j + 2] - (acc[j] + s_bias[g * 32 + j])) * expf(-(acc[j + 1] + s_bias[g * 32 + j + 1]));
+            vin[3] = (xin[j + 3] - (acc[j + 2] + s_bias[g * 32 + j + 2])) * expf(-(acc[j + 3] + s_bias[g * 32 + j + 3]));
 #pragma unroll
             for (int o = 0; o < 4; ++o) {
               float z = wi[o * 4 + 0] * vin[0];
               z = fmaf(wi[o * 4 + 1], vin[1], z);
               z = fmaf(wi[o * 4 + 2], vin[2], z);
               z = fmaf(wi[o * 4 + 3], vin[3], z);
-              sb[(size_t)ch[o] * p.y_ld] = (z - __ldg(p.an_bias + ch[o])) * __ldg(p.an_scale + ch[o]);
+              sb[(size_t)ch[o] * p.y_ld] = (z - s_anb[ch[o]]) * s_ans[ch[o]];
             }
           }
         }
       }
     }
   }
+  if (tid == 0) UM_TRACE(7);
   tc_fence_before();
   __syncthreads();
   if (warp == 8) tmem_dealloc(tmem, tmem_cols);
+  if (tid == 0) UM_TRACE(8);
 }
 
 }  // namespace b2

@@ -273,6 +273,24 @@ static void conv(b200tts_call* c, ConvParams& p, const ConvW& w, int batch, int 
     p.wu = w.wu;
     p.um_nt = w.nt;
     p.um_nsplit = w.nsplit;
+    static int trace = -1;
+    if (trace < 0) trace = getenv("B200TTS_CONV_TRACE") ? 1 : 0;
+    if (trace) {  // debug: per-phase timestamps of CTA (0,0,0), one line per conv on stderr (serialises the stream)
+      static unsigned long long* dbg = nullptr;
+      static unsigned long long last_end = 0;
+      if (!dbg) B2_CUDA(cudaMallocManaged(&dbg, 16 * sizeof(unsigned long long)));
+      B2_CUDA(cudaDeviceSynchronize());
+      memset(dbg, 0, 16 * sizeof(unsigned long long));
+      p.dbg = dbg;
+      c->launches += launch_conv_umma(p, batch, Lmax, s);
+      B2_CUDA(cudaDeviceSynchronize());
+      fprintf(stderr, "[conv] Cin %4d Cout %4d K %2d L %6d nt %3d | gap %6.1f prologue %5.1f A0 %5.1f mma0 %5.1f issued %6.1f Alast %6.1f acc %6.1f epi %5.1f end %5.1f | total %6.1f us\n",
+              p.Cin, p.Cout, p.K, Lmax, p.um_nt, last_end ? (dbg[0] - last_end) * 1e-3 : 0.0, (dbg[1] - dbg[0]) * 1e-3, (dbg[2] - dbg[1]) * 1e-3,
+              (dbg[3] - dbg[1]) * 1e-3, (dbg[4] - dbg[1]) * 1e-3, (dbg[5] - dbg[1]) * 1e-3, (dbg[6] - dbg[1]) * 1e-3, (dbg[7] - dbg[6]) * 1e-3,
+              (dbg[8] - dbg[7]) * 1e-3, (dbg[8] - dbg[0]) * 1e-3);
+      last_end = dbg[8];
+      return;
+    }
     c->launches += launch_conv_umma(p, batch, Lmax, s);
   } else {
     B2_CHECK(w.w != nullptr, "layer has no fp32 weights for the SIMT path");

@@ -351,8 +351,9 @@ def bench_ours(args, rank, world, local_rank):
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": voc_tflops, "peak": tensor_peak, "unit": "TFLOP/s",
                          "frac": voc_tflops / tensor_peak, "traffic": None, "peak_source": peak_src + " bf16 dense (burst)",
-                         "kernel": f"conv1d_kernel<BM,BN,TM,TN> fp32 SIMT implicit GEMM: HiFi-GAN pass ({voc_launches} launches, {vms:.3f} ms, "
-                                   f"{HIFIGAN_MFLOP_PER_FRAME:.1f} MFLOP/frame x {frames} frames)",
+                         "kernel": f"conv_umma_kernel<MT,NSPLIT,EW,WST> (tcgen05 kind::f16, bf16x3 split = 3 MMAs per algorithmic MAC-tile, fp32 TMEM "
+                                   f"accumulators): HiFi-GAN pass ({voc_launches} launches, {vms:.3f} ms, {HIFIGAN_MFLOP_PER_FRAME:.1f} MFLOP/frame x {frames} frames)",
+                         "tensor_flops_issued_tflops": 3 * voc_tflops, "frac_tensor_issued": 3 * voc_tflops / tensor_peak,
                          "fp32_simt_peak_tflops": FP32_SIMT_PEAK_TFLOPS, "frac_of_fp32_simt_peak": voc_tflops / FP32_SIMT_PEAK_TFLOPS,
                          "step_tflops": step_flops / (ms_per_step * 1e-3) / 1e12,
                          "hbm_compulsory_gbs": (170.0e6 + 8 * N_IDS + 832 * frames) / (ms_per_step * 1e-3) / 1e9,

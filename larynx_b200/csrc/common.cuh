@@ -81,6 +81,16 @@ struct ConvParams {
   const void* wu = nullptr;
   int um_nt = 0, um_nsplit = 2, pix = 1;
   unsigned long long* dbg = nullptr;  // optional per-phase %globaltimer trace of CTA (0,0,0)
+  // bf16 plane images (conv_umma.cuh): xp = input image written by the producing layer (enables bulk-copy A),
+  // yp / yp2 = images this launch writes for its consumers (yp2: the WN skip accumulator of EPI_RESSKIP)
+  const void* xp = nullptr;
+  long long xp_bs = 0;  // bytes between batch items
+  int xp_kc = 0, xp_rows = 0;
+  void* yp = nullptr;
+  void* yp2 = nullptr;
+  long long yp_bs = 0;
+  int yp_kc = 0, yp_rows = 0, yp_nsplit = 2;
+  float yp_slope = 1.f;  // planes hold v > 0 ? v : v*slope (the consumer's LeakyReLU); 1 = identity
 };
 
 }  // namespace b2

@@ -1,20 +1,27 @@
 // conv_umma.cuh — Conv1d as an implicit GEMM on the 5th-gen tensor cores (tcgen05, accumulators in TMEM)
-// with fp32-class accuracy from a bf16 split:  x = hi + lo (+ lo2),  D += Ahi*Bhi + Alo*Bhi + Ahi*Blo (+ ...)
+// with fp32-class accuracy from a bf16 split:  x = hi + lo (+ lo2),  D = Ahi*Bhi + (Ahi*Blo + Alo*Bhi) (+ ...)
 //
 //   D[t][co] = sum_k sum_ci  X[ci][t + k*dil - pad_left] * W[co][ci][k]
-//   M = time (128 rows per MMA, MT tiles per CTA), N = output channels (NT <= 256 per CTA), K = input channels
+//   M = time (128 rows per MMA, MT tiles per CTA), N = output channels (NT <= 128 per CTA), K = input channels
 //
-// One CTA:
-//   warps 0..7  : A producers — read fp32 activations [C][L] from global (coalesced along time), apply the fused
-//                 pre-op (MRF mean of 3 inputs, LeakyReLU, zero padding by valid length), split to bf16 hi/lo and
-//                 write the UMMA operand image [k-chunk][row][8] (K-major, SWIZZLE_NONE, SBO = 128 B) to smem;
-//                 after the main loop the same warps run the epilogue: TMEM -> registers (tcgen05.ld 32x32b) ->
-//                 bias / act / residual / gate / WN res-skip / coupling+invconv+actnorm / pixel-shuffle -> global.
-//   warp 8      : MMA issuer (one elected lane): tcgen05.mma.cta_group::1.kind::f16, tap k = same A image with the
-//                 descriptor start address advanced by k*dil rows (16 B each) — no im2col, no per-tap copies.
-//   warp 9      : weight producer: one cp.async.bulk (TMA engine) per (ci-chunk, tap) stage from the pre-packed bf16
-//                 hi/lo image, completion on an mbarrier.
-// Pipelines: A ring (2 stages, per ci-chunk of 32 channels, reused by all K taps), W ring (4 stages, per tap),
+// Operand images.  Both MMA operands are K-major, SWIZZLE_NONE with SBO = 128 B, i.e. [k-chunk of 8][row][8 bf16]:
+// the address is linear in the row, so conv tap k is the SAME activation image with the descriptor start address
+// advanced by k*dil rows (16 B each) — no im2col, no per-tap copies.
+//   * weights: pre-split bf16 image per (n-tile, ci-chunk, tap), one cp.async.bulk (TMA engine) per stage;
+//   * activations, "plane" mode: the PRODUCING layer's epilogue already wrote the bf16 hi/lo planes of its
+//     (pre-activated) output in image order [plane][C/8][PADL + rows][8] to global memory, so the consumer's A
+//     tile is 2*4 contiguous bulk copies per 32-channel chunk — no SM instructions on the operand path;
+//   * activations, "gather" mode (inputs produced by non-conv kernels, or needing the MRF mean of 3 tensors):
+//     warps 0..7 read fp32 [C][L], apply the pre-op, split and write the image to smem themselves.
+//
+// One CTA (320 threads):
+//   warps 0..7 : gather-mode A producers during the main loop; afterwards the epilogue:
+//                TMEM -> registers (tcgen05.ld 32x32b) -> bias / act / residual / tanh*sigmoid gate / WN res-skip /
+//                affine coupling + InvConvNear^-1 + ActNorm^-1 / pixel shuffle -> fp32 [C][L] (+ bf16 planes for the
+//                next conv, including the zero rows that implement the reference's padding/masking);
+//   warp 8     : MMA issuer (one lane): tcgen05.mma.cta_group::1.kind::f16, one accumulator per magnitude class;
+//   warp 9     : lane 0 weight bulk copies; (plane mode) thread 0 issues the activation bulk copies.
+// Pipelines: A ring (2 stages, per ci-chunk of 32 channels, reused by all K taps), W ring (3 stages, per tap),
 // accumulator barrier (MMA -> epilogue).  All waits are mbarrier based; tcgen05.commit releases stages.
 #pragma once
 #include "common.cuh"
@@ -25,18 +32,21 @@ namespace b2 {
 constexpr int UM_BKC = 32;               // input channels per A stage
 constexpr int UM_KCH = UM_BKC / 8;       // 16-byte k-chunks per stage
 constexpr int UM_HALO = 80;              // max (K-1)*dil
-constexpr int UM_WSTAGES = 3;
 constexpr int UM_ASTAGES = 2;
-constexpr int UM_NPROD = 256;            // producer / epilogue threads (8 warps)
-constexpr int UM_NT_THREADS = UM_NPROD + 64;
+constexpr int UM_WSTAGES_MAX = 8;
+constexpr int UM_PADL = 40;              // zero rows in front of a plane image (>= any pad_left)
+constexpr int UM_TAIL = 128;             // zero rows written behind the last tile (>= UM_HALO)
+
+// rows (per 8-channel group) a plane image must provide for a tensor of max length L
+__host__ __device__ inline int um_plane_rows(int L) { return UM_PADL + (L + 255) / 256 * 256 + UM_TAIL + 128; }
 
 template <int MT>
 struct UmmaCfg {
   static constexpr int RA = MT * 128 + UM_HALO;  // rows of the A image
   static size_t a_stage_bytes(int nsplit) { return (size_t)nsplit * UM_KCH * RA * 16; }
   static size_t w_stage_bytes(int nsplit, int NT) { return (size_t)nsplit * UM_KCH * NT * 16; }
-  static size_t smem_bytes(int nsplit, int NT) {
-    return UM_ASTAGES * a_stage_bytes(nsplit) + UM_WSTAGES * w_stage_bytes(nsplit, NT) + 128 + 4 * (256 + 16 + 2 * 256);
+  static size_t smem_bytes(int nsplit, int NT, int wstages) {
+    return UM_ASTAGES * a_stage_bytes(nsplit) + wstages * w_stage_bytes(nsplit, NT) + 256 + 4 * (256 + 16 + 2 * 256);
   }
 };
 
@@ -45,8 +55,8 @@ __device__ __forceinline__ unsigned long long gtimer() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-#define UM_TRACE(slot)                                                                         \
-  do {                                                                                         \
+#define UM_TRACE(slot)                                                                           \
+  do {                                                                                           \
     if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.dbg[slot] = gtimer(); \
   } while (0)
 
@@ -54,27 +64,111 @@ __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
 
-template <int MT, int NSPLIT>
-__global__ void __launch_bounds__(UM_NT_THREADS, MT == 1 ? 2 : 1) conv_umma_kernel(const ConvParams p) {
+// split 8 floats into NSPLIT bf16 planes, 16 bytes each
+// two floats -> packed bf16x2 (one cvt.rn.bf16x2.f32), low half = a
+__device__ __forceinline__ uint32_t cvt_bf16x2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+template <int NSPLIT>
+__device__ __forceinline__ void split8(const float* v, uint4* out) {
+  uint32_t h[4], l[4], l2[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float a = v[2 * e], b = v[2 * e + 1];
+    h[e] = cvt_bf16x2(a, b);
+    const float ra = a - __uint_as_float(h[e] << 16), rb = b - __uint_as_float(h[e] & 0xffff0000u);
+    l[e] = cvt_bf16x2(ra, rb);
+    if (NSPLIT == 3) l2[e] = cvt_bf16x2(ra - __uint_as_float(l[e] << 16), rb - __uint_as_float(l[e] & 0xffff0000u));
+  }
+  out[0] = make_uint4(h[0], h[1], h[2], h[3]);
+  out[1] = make_uint4(l[0], l[1], l[2], l[3]);
+  if (NSPLIT == 3) out[2] = make_uint4(l2[0], l2[1], l2[2], l2[3]);
+}
+
+// A plane image in global memory (written by epilogues, read by bulk copies)
+struct PlaneOut {
+  unsigned char* base;  // item base
+  int kc_total, rows, nsplit;
+  float slope;          // value stored = v > 0 ? v : v*slope  (1 = identity)
+  // zero-row bookkeeping of the calling thread
+  bool pad_front;       // this CTA owns t = [-PADL, 0)
+  bool pad_tail;        // this CTA owns the UM_TAIL rows behind its tile
+  int m;                // thread's row index inside the CTA tile (0 .. MT*128-1)
+  long long tail_row0;  // first tail row (image row index, includes PADL)
+  __device__ __forceinline__ unsigned char* at(int plane, int kc, long long row) const {
+    return base + (((size_t)plane * kc_total + kc) * rows + row) * 16;
+  }
+};
+
+// store 8 consecutive channels (one 16-byte chunk per plane) of image row `row` (+ this thread's share of zero rows)
+__device__ __forceinline__ void plane_store8(const PlaneOut& po, int kc, long long row, const float* v8) {
+  float w[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) w[e] = v8[e] > 0.f ? v8[e] : v8[e] * po.slope;
+  uint4 q[3];
+  if (po.nsplit == 3) split8<3>(w, q);
+  else split8<2>(w, q);
+  const uint4 z = make_uint4(0, 0, 0, 0);
+  for (int pl = 0; pl < po.nsplit; ++pl) {
+    *reinterpret_cast<uint4*>(po.at(pl, kc, row)) = q[pl];
+    if (po.pad_front && po.m < UM_PADL) *reinterpret_cast<uint4*>(po.at(pl, kc, po.m)) = z;
+    if (po.pad_tail && po.m < UM_TAIL) *reinterpret_cast<uint4*>(po.at(pl, kc, po.tail_row0 + po.m)) = z;
+  }
+}
+// store 4 consecutive channels (8 bytes at byte offset `boff` inside the 16-byte chunk); no zero-row duty
+__device__ __forceinline__ void plane_store4(const PlaneOut& po, int kc, int boff, long long row, const float* v4) {
+  for (int pl = 0; pl < po.nsplit; ++pl) {
+    uint32_t q[2];
+#pragma unroll
+    for (int e = 0; e < 4; e += 2) {
+      float a0 = v4[e] > 0.f ? v4[e] : v4[e] * po.slope, a1 = v4[e + 1] > 0.f ? v4[e + 1] : v4[e + 1] * po.slope;
+      for (int s = 0; s < pl; ++s) {  // peel the planes above this one
+        a0 -= __bfloat162float(__float2bfloat16_rn(a0));
+        a1 -= __bfloat162float(__float2bfloat16_rn(a1));
+      }
+      q[e >> 1] = pack_bf16x2(__float2bfloat16_rn(a0), __float2bfloat16_rn(a1));
+    }
+    *reinterpret_cast<uint2*>(po.at(pl, kc, row) + boff) = make_uint2(q[0], q[1]);
+  }
+}
+
+// MT: 128-row tiles per CTA; NSPLIT: bf16 planes per operand; EW: epilogue/gather warps (8 or 16);
+// WST: weight ring depth.  <1,2,8,3> fits two CTAs per SM (large grids); EW = 16 variants are for small grids
+// where a CTA has the SM to itself and the serial latency of one tile is what matters.
+template <int MT, int NSPLIT, int EW, int WST>
+__global__ void __launch_bounds__(EW * 32 + 64, (MT == 1 && EW == 8) ? 2 : 1) conv_umma_kernel(const ConvParams p) {
   using namespace umma;
   using C = UmmaCfg<MT>;
   constexpr int RA = C::RA;
+  constexpr int UM_WSTAGES = WST;
+  constexpr int UM_NPROD = EW * 32;
+  constexpr int UM_NT_THREADS = UM_NPROD + 64;
+  constexpr int W_MMA = EW, W_LOAD = EW + 1;
+  static_assert(WST <= UM_WSTAGES_MAX, "weight ring too deep");
+  constexpr int NACC = NSPLIT;  // one fp32 accumulator per magnitude class of split products: the tensor core
+                                // truncates when it adds into the accumulator, so the long hi*hi chain must not
+                                // absorb the small cross terms
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int NT = p.um_nt;
-  const uint32_t a_split_bytes = UM_KCH * RA * 16;          // one split plane (hi or lo) of an A stage
+  const uint32_t a_split_bytes = UM_KCH * RA * 16;  // one split plane (hi or lo) of an A stage
   const uint32_t a_stage = NSPLIT * a_split_bytes;
   const uint32_t w_split_bytes = UM_KCH * NT * 16;
   const uint32_t w_stage = NSPLIT * w_split_bytes;
   unsigned char* sA = smem_raw;
   unsigned char* sW = smem_raw + UM_ASTAGES * a_stage;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sW + UM_WSTAGES * w_stage);
-  uint64_t* a_full = bars;                      // [2]
-  uint64_t* a_empty = bars + 2;                 // [2]
-  uint64_t* w_full = bars + 4;                  // [UM_WSTAGES]
-  uint64_t* w_empty = bars + 8;                 // [UM_WSTAGES]
-  uint64_t* acc_full = bars + 12;               // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
-  float* s_bias = reinterpret_cast<float*>(bars + 16);  // [NT] bias of this N tile (+ [16+2*half] coupling constants)
+  uint64_t* a_full = bars;        // [2]
+  uint64_t* a_empty = bars + 2;   // [2]
+  uint64_t* w_full = bars + 4;    // [UM_WSTAGES]
+  uint64_t* w_empty = bars + 12;  // [UM_WSTAGES]
+  uint64_t* acc_full = bars + 20; // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+  float* s_bias = reinterpret_cast<float*>(bars + 32);  // [NT] bias of this N tile
+  float* s_inv = s_bias + 256;                          // [16]      coupling: W^-1
+  float* s_anb = s_inv + 16;                            // [2*half]  ActNorm bias
+  float* s_ans = s_anb + 256;                           // [2*half]  ActNorm exp(-logs)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.z;
@@ -85,16 +179,14 @@ __global__ void __launch_bounds__(UM_NT_THREADS, MT == 1 ? 2 : 1) conv_umma_kern
   if (t0 >= Lb) return;
   const int K = p.K, dil = p.dil;
   const int nch = (p.Cin + UM_BKC - 1) / UM_BKC;
+  const bool planes_in = p.xp != nullptr;
   uint32_t tmem_cols = 32;
-  // one fp32 accumulator per magnitude class of split products (hi*hi | hi*lo+lo*hi | ...): the tensor core
-  // truncates when it adds into the accumulator, so the long hi*hi chain must not absorb the small terms
-  constexpr int NACC = NSPLIT;
   while (tmem_cols < (uint32_t)(NACC * MT * NT)) tmem_cols <<= 1;
 
   if (tid == 0) UM_TRACE(0);
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&a_full[i], UM_NPROD / 32);
+      mbar_init(&a_full[i], planes_in ? 1 : UM_NPROD / 32);
       mbar_init(&a_empty[i], 1);
     }
     for (int i = 0; i < UM_WSTAGES; ++i) {
@@ -104,12 +196,9 @@ __global__ void __launch_bounds__(UM_NT_THREADS, MT == 1 ? 2 : 1) conv_umma_kern
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc(tmem_slot, tmem_cols);
+  if (warp == W_MMA) tmem_alloc(tmem_slot, tmem_cols);
   // epilogue constants -> smem (global loads in the epilogue would serialise on L2 latency)
   for (int i = tid; i < NT; i += UM_NT_THREADS) s_bias[i] = (n0 + i) < p.Cout ? p.bias[n0 + i] : 0.f;
-  float* s_inv = s_bias + 256;        // [16]
-  float* s_anb = s_inv + 16;          // [2*half] ActNorm bias
-  float* s_ans = s_anb + 256;         // [2*half] ActNorm exp(-logs)
   if (p.epi == EPI_COUPLING) {
     if (tid < 16) s_inv[tid] = p.inv_w[tid];
     for (int i = tid; i < 2 * p.half; i += UM_NT_THREADS) {
@@ -123,7 +212,7 @@ __global__ void __launch_bounds__(UM_NT_THREADS, MT == 1 ? 2 : 1) conv_umma_kern
   const uint32_t tmem = *tmem_slot;
   if (tid == 0) UM_TRACE(1);
 
-  if (warp == 9) {
+  if (warp == W_LOAD) {
     // ===================== weight producer =====================
     if (lane == 0) {
       const unsigned char* gw = reinterpret_cast<const unsigned char*>(p.wu) + (size_t)ntile * nch * K * w_stage;
@@ -136,7 +225,7 @@ __global__ void __launch_bounds__(UM_NT_THREADS, MT == 1 ? 2 : 1) conv_umma_kern
           bulk_g2s(sW + (size_t)s * w_stage, gw + (size_t)n * w_stage, w_stage, &w_full[s]);
         }
     }
-  } else if (warp == 8) {
+  } else if (warp == W_MMA) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16_f32(128, NT);
@@ -184,102 +273,128 @@ __global__ void __launch_bounds__(UM_NT_THREADS, MT == 1 ? 2 : 1) conv_umma_kern
       UM_TRACE(4);
     }
   } else {
-    // ===================== A producers (warps 0..7) =====================
-    const float* xb = p.x + (size_t)b * p.x_bs;
-    const float* xb2 = p.x2 ? p.x2 + (size_t)b * p.x_bs : nullptr;
-    const float* xb3 = p.x3 ? p.x3 + (size_t)b * p.x_bs : nullptr;
-    const int rows_used = MT * 128 + (K - 1) * dil;
-    const bool three = xb2 != nullptr && xb3 != nullptr;  // MRF mean of three inputs (uniform)
-    for (int c = 0; c < nch; ++c) {
-      const int as = c & 1;
-      mbar_wait(&a_empty[as], ((c >> 1) & 1) ^ 1);
-      unsigned char* dst = sA + (size_t)as * a_stage;
-      constexpr int NTASK = (UM_KCH * RA + UM_NPROD - 1) / UM_NPROD;
-      constexpr int TB = MT == 1 ? 4 : 3;  // tasks per batch: TB x 8 independent global loads in flight per thread
-#pragma unroll 1
-      for (int i0 = 0; i0 < NTASK; i0 += TB) {
-        float v[TB][8];
-        int so[TB];
-        // branch-free gather: every load is unconditional (clamped to a safe address) and masked afterwards,
-        // so all TB*8 loads of a batch are in flight together
+    if (planes_in) {
+      // ===================== A by bulk copy from the producer's plane image =====================
+      if (tid == 0) {
+        const unsigned char* xp = reinterpret_cast<const unsigned char*>(p.xp) + (size_t)b * p.xp_bs;
+        const long long row0 = (long long)t0 - p.pad_left + UM_PADL;
+        for (int c = 0; c < nch; ++c) {
+          const int as = c & 1;
+          mbar_wait(&a_empty[as], ((c >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(&a_full[as], a_stage);
+          unsigned char* dst = sA + (size_t)as * a_stage;
+          for (int sp = 0; sp < NSPLIT; ++sp)
 #pragma unroll
-        for (int i = 0; i < TB; ++i) {
-          const int task = tid + (i0 + i) * UM_NPROD;
-          const int kc = task / RA, r = task - kc * RA;
-          const int tin = t0 - p.pad_left + r;
-          const bool row_ok = task < UM_KCH * RA && r < rows_used && tin >= 0 && tin < Lb;
-          const int ci0 = c * UM_BKC + kc * 8;
-          so[i] = task < UM_KCH * RA ? (kc * RA + r) * 16 : -1;
-          const int tin_c = row_ok ? tin : 0;
-          if (!three) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const bool ok = row_ok && (ci0 + e) < p.Cin;
-              const size_t off = ok ? (size_t)(ci0 + e) * p.x_ld + tin_c : 0;
-              const float a = __ldg(xb + off);
-              v[i][e] = ok ? a : 0.f;
-            }
-          } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const bool ok = row_ok && (ci0 + e) < p.Cin;
-              const size_t off = ok ? (size_t)(ci0 + e) * p.x_ld + tin_c : 0;
-              const float a = __ldg(xb + off), a2 = __ldg(xb2 + off), a3 = __ldg(xb3 + off);
-              v[i][e] = ok ? (a + a2) + a3 : 0.f;
-            }
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < TB; ++i) {
-          if (so[i] < 0) continue;
-          __nv_bfloat16 h[8], l[8], l2[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            float a = v[i][e];
-            if (p.in_div != 1.f) a = a / p.in_div;
-            if (p.pre == PRE_LRELU) a = a > 0.f ? a : a * p.pre_slope;
-            h[e] = __float2bfloat16_rn(a);
-            const float r1 = a - __bfloat162float(h[e]);
-            l[e] = __float2bfloat16_rn(r1);
-            if (NSPLIT == 3) l2[e] = __float2bfloat16_rn(r1 - __bfloat162float(l[e]));
-          }
-          unsigned char* o = dst + so[i];
-          *reinterpret_cast<uint4*>(o) =
-              make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
-          *reinterpret_cast<uint4*>(o + a_split_bytes) =
-              make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]), pack_bf16x2(l[4], l[5]), pack_bf16x2(l[6], l[7]));
-          if (NSPLIT == 3)
-            *reinterpret_cast<uint4*>(o + 2 * a_split_bytes) = make_uint4(
-                pack_bf16x2(l2[0], l2[1]), pack_bf16x2(l2[2], l2[3]), pack_bf16x2(l2[4], l2[5]), pack_bf16x2(l2[6], l2[7]));
+            for (int kc = 0; kc < UM_KCH; ++kc)
+              bulk_g2s(dst + sp * a_split_bytes + kc * RA * 16,
+                       xp + (((size_t)sp * p.xp_kc + c * UM_KCH + kc) * p.xp_rows + row0) * 16, RA * 16, &a_full[as]);
+          if (c == 0) UM_TRACE(2);
+          if (c == nch - 1) UM_TRACE(5);
         }
       }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&a_full[as]);
-      if (tid == 0 && c == 0) UM_TRACE(2);
-      if (tid == 0 && c == nch - 1) UM_TRACE(5);
+    } else {
+      // ===================== A by gather + split (warps 0..7) =====================
+      const float* xb = p.x + (size_t)b * p.x_bs;
+      const float* xb2 = p.x2 ? p.x2 + (size_t)b * p.x_bs : nullptr;
+      const float* xb3 = p.x3 ? p.x3 + (size_t)b * p.x_bs : nullptr;
+      const int rows_used = MT * 128 + (K - 1) * dil;
+      const bool three = xb2 != nullptr && xb3 != nullptr;  // MRF mean of three inputs (uniform)
+      for (int c = 0; c < nch; ++c) {
+        const int as = c & 1;
+        mbar_wait(&a_empty[as], ((c >> 1) & 1) ^ 1);
+        unsigned char* dst = sA + (size_t)as * a_stage;
+        constexpr int NTASK = (UM_KCH * RA + UM_NPROD - 1) / UM_NPROD;
+        constexpr int TB = NTASK < 4 ? NTASK : (MT == 1 ? 4 : 3);  // tasks per batch: TB x 8 loads in flight per thread
+#pragma unroll 1
+        for (int i0 = 0; i0 < NTASK; i0 += TB) {
+          float v[TB][8];
+          int so[TB];
+          // branch-free gather: every load is unconditional (clamped to a safe address) and masked afterwards,
+          // so all TB*8 loads of a batch are in flight together
+#pragma unroll
+          for (int i = 0; i < TB; ++i) {
+            const int task = tid + (i0 + i) * UM_NPROD;
+            const int kc = task / RA, r = task - kc * RA;
+            const int tin = t0 - p.pad_left + r;
+            const bool row_ok = task < UM_KCH * RA && r < rows_used && tin >= 0 && tin < Lb;
+            const int ci0 = c * UM_BKC + kc * 8;
+            so[i] = task < UM_KCH * RA ? (kc * RA + r) * 16 : -1;
+            const int tin_c = row_ok ? tin : 0;
+            if (!three) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const bool ok = row_ok && (ci0 + e) < p.Cin;
+                const size_t off = ok ? (size_t)(ci0 + e) * p.x_ld + tin_c : 0;
+                const float a = __ldg(xb + off);
+                v[i][e] = ok ? a : 0.f;
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const bool ok = row_ok && (ci0 + e) < p.Cin;
+                const size_t off = ok ? (size_t)(ci0 + e) * p.x_ld + tin_c : 0;
+                const float a = __ldg(xb + off), a2 = __ldg(xb2 + off), a3 = __ldg(xb3 + off);
+                v[i][e] = ok ? (a + a2) + a3 : 0.f;
+              }
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < TB; ++i) {
+            if (so[i] < 0) continue;
+            float w[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              float a = v[i][e];
+              if (p.in_div != 1.f) a = a / p.in_div;
+              if (p.pre == PRE_LRELU) a = a > 0.f ? a : a * p.pre_slope;
+              w[e] = a;
+            }
+            uint4 q[3];
+            split8<NSPLIT>(w, q);
+            unsigned char* o = dst + so[i];
+#pragma unroll
+            for (int sp = 0; sp < NSPLIT; ++sp) *reinterpret_cast<uint4*>(o + sp * a_split_bytes) = q[sp];
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_full[as]);
+        if (tid == 0 && c == 0) UM_TRACE(2);
+        if (tid == 0 && c == nch - 1) UM_TRACE(5);
+      }
     }
 
-    // ===================== epilogue (same warps) =====================
+    // ===================== epilogue (warps 0..7) =====================
     mbar_wait(acc_full, 0);
     tc_fence_after();
     if (tid == 0) UM_TRACE(6);
-    const int quad = warp & 3;
-    const int grp = warp >> 2;  // MT == 2: the M tile; MT == 1: which half of the N columns
-    const int mt = MT == 2 ? grp : 0;
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+    const int wset = warp >> 2; // EW/4 warp sets share the (M tile, column group) work
+    const int mt = MT == 2 ? (wset & 1) : 0;
+    const int cset = MT == 2 ? (wset >> 1) : wset;       // column-group residue owned by this warp set
+    constexpr int NCSET = MT == 2 ? EW / 8 : EW / 4;
     const int m = quad * 32 + lane;
     const int t = t0 + mt * 128 + m;
     const bool t_ok = t < Lb;
     const int ngroups = (NT + 31) / 32;
-    const int g_lo = MT == 2 ? 0 : (grp == 0 ? 0 : (ngroups + 1) / 2);
-    const int g_hi = MT == 2 ? ngroups : (grp == 0 ? (ngroups + 1) / 2 : ngroups);
-    for (int g = g_lo; g < g_hi; ++g) {
+    const int u = p.pix > 1 ? p.pix : 1;
+    // plane outputs: primary (yp) and, for EPI_RESSKIP, the skip accumulator (yp2)
+    PlaneOut po, po2;
+    po.base = p.yp ? reinterpret_cast<unsigned char*>(p.yp) + (size_t)b * p.yp_bs : nullptr;
+    po.kc_total = p.yp_kc; po.rows = p.yp_rows; po.nsplit = p.yp_nsplit; po.slope = p.yp_slope;
+    po.pad_front = blockIdx.x == 0;
+    po.pad_tail = (long long)(t0 + MT * 128) >= Lb;
+    po.m = mt * 128 + m;
+    po.tail_row0 = (long long)UM_PADL + (long long)(t0 + MT * 128) * u;
+    po2 = po;
+    po2.base = p.yp2 ? reinterpret_cast<unsigned char*>(p.yp2) + (size_t)b * p.yp_bs : nullptr;
+
+    for (int g = cset; g < ngroups; g += NCSET) {
       float acc[32];
       {
         uint32_t raw[32];
         const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * 32);
-        // smallest magnitude class first
-        tmem_ld32(lane_addr + (uint32_t)(((NACC - 1) * MT + mt) * NT), raw);
+        tmem_ld32(lane_addr + (uint32_t)(((NACC - 1) * MT + mt) * NT), raw);  // smallest magnitude class first
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(raw[j]);
@@ -293,11 +408,11 @@ __global__ void __launch_bounds__(UM_NT_THREADS, MT == 1 ? 2 : 1) conv_umma_kern
       }
       const int nb = n0 + g * 32;  // packed channel of acc[0]
       const int jmax = min(32, min(NT - g * 32, p.Cout - nb));
-      if (!t_ok || jmax <= 0) continue;
-      if (p.epi == EPI_PLAIN && p.pix <= 1) {
+      if (jmax <= 0) continue;
+      if (p.epi == EPI_PLAIN && u == 1) {
         float* __restrict__ yb = p.y + (size_t)b * p.y_bs + t;
         float rv[32];
-        if (p.res) {
+        if (p.res && t_ok) {
           const float* __restrict__ rb = p.res + (size_t)b * p.res_bs + t;
 #pragma unroll
           for (int j = 0; j < 32; ++j) rv[j] = rb[(size_t)(nb + (j < jmax ? j : 0)) * p.res_ld];
@@ -307,111 +422,206 @@ __global__ void __launch_bounds__(UM_NT_THREADS, MT == 1 ? 2 : 1) conv_umma_kern
         }
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          if (j < jmax) {
-            float v = acc[j] + s_bias[g * 32 + j];
-            if (p.act == ACT_RELU) v = fmaxf(v, 0.f);
-            else if (p.act == ACT_TANH) v = tanhf(v);
-            yb[(size_t)(nb + j) * p.y_ld] = v + rv[j];
-          }
+          float v = acc[j] + s_bias[g * 32 + j];
+          if (p.act == ACT_RELU) v = fmaxf(v, 0.f);
+          else if (p.act == ACT_TANH) v = tanhf(v);
+          v += rv[j];
+          acc[j] = (t_ok && j < jmax) ? v : 0.f;
+        }
+        if (t_ok && p.y) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < jmax) yb[(size_t)(nb + j) * p.y_ld] = acc[j];
+        }
+        if (po.base) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (q * 8 < jmax) plane_store8(po, (nb >> 3) + q, (long long)UM_PADL + t, acc + q * 8);
         }
       } else if (p.epi == EPI_PLAIN) {
         // pixel shuffle (transposed conv): packed channel n = co*u + r -> y[co][t*u + r]
         float* __restrict__ yb = p.y + (size_t)b * p.y_bs;
-        const int u = p.pix;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j] += j < jmax ? s_bias[g * 32 + j] : 0.f;
-        if (u == 8 && jmax == 32) {
+        for (int j = 0; j < 32; ++j) acc[j] = (t_ok && j < jmax) ? acc[j] + s_bias[g * 32 + j] : 0.f;
+        if (t_ok) {
+          if (u == 8 && jmax == 32) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float4* d = reinterpret_cast<float4*>(yb + (size_t)(nb / 8 + q) * p.y_ld + (size_t)t * 8);
-            d[0] = make_float4(acc[q * 8 + 0], acc[q * 8 + 1], acc[q * 8 + 2], acc[q * 8 + 3]);
-            d[1] = make_float4(acc[q * 8 + 4], acc[q * 8 + 5], acc[q * 8 + 6], acc[q * 8 + 7]);
+            for (int q = 0; q < 4; ++q) {
+              float4* d = reinterpret_cast<float4*>(yb + (size_t)(nb / 8 + q) * p.y_ld + (size_t)t * 8);
+              d[0] = make_float4(acc[q * 8 + 0], acc[q * 8 + 1], acc[q * 8 + 2], acc[q * 8 + 3]);
+              d[1] = make_float4(acc[q * 8 + 4], acc[q * 8 + 5], acc[q * 8 + 6], acc[q * 8 + 7]);
+            }
+          } else if (u == 4 && jmax == 32) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<float4*>(yb + (size_t)(nb / 4 + q) * p.y_ld + (size_t)t * 4) =
+                  make_float4(acc[q * 4 + 0], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]);
+          } else if (u == 2 && jmax == 32) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q)
+              *reinterpret_cast<float2*>(yb + (size_t)(nb / 2 + q) * p.y_ld + (size_t)t * 2) = make_float2(acc[q * 2], acc[q * 2 + 1]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (j < jmax) {
+                const int n = nb + j, co = n / u, r = n - co * u;
+                yb[(size_t)co * p.y_ld + (size_t)t * u + r] = acc[j];
+              }
+            }
           }
-        } else if (u == 4 && jmax == 32) {
+        }
+        if (po.base && jmax == 32) {
+          const long long orow = (long long)UM_PADL + (long long)t * u;
+          if (u == 2) {  // 16 channels x 2 phases: two full chunks per output row
 #pragma unroll
-          for (int q = 0; q < 8; ++q)
-            *reinterpret_cast<float4*>(yb + (size_t)(nb / 4 + q) * p.y_ld + (size_t)t * 4) =
-                make_float4(acc[q * 4 + 0], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]);
-        } else if (u == 2 && jmax == 32) {
+            for (int r = 0; r < 2; ++r)
 #pragma unroll
-          for (int q = 0; q < 16; ++q)
-            *reinterpret_cast<float2*>(yb + (size_t)(nb / 2 + q) * p.y_ld + (size_t)t * 2) = make_float2(acc[q * 2], acc[q * 2 + 1]);
-        } else {
+              for (int h = 0; h < 2; ++h) {
+                float v8[8];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (j < jmax) {
-              const int n = nb + j, co = n / u, r = n - co * u;
-              yb[(size_t)co * p.y_ld + (size_t)t * u + r] = acc[j];
+                for (int e = 0; e < 8; ++e) v8[e] = acc[(h * 8 + e) * 2 + r];
+                PlaneOut pr = po;  // the zero rows are emitted once, with phase 0
+                if (r) pr.pad_front = pr.pad_tail = false;
+                plane_store8(pr, (nb >> 4) + h, orow + r, v8);
+              }
+          } else if (u == 4) {  // 8 channels x 4 phases
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              float v8[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v8[e] = acc[e * 4 + r];
+              PlaneOut pr = po;
+              if (r) pr.pad_front = pr.pad_tail = false;
+              plane_store8(pr, nb >> 5, orow + r, v8);
+            }
+          } else if (u == 8) {  // 4 channels x 8 phases: half chunks
+            const int co0 = nb >> 3;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              float v4[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) v4[e] = acc[e * 8 + r];
+              plane_store4(po, co0 >> 3, (co0 & 7) * 2, orow + r, v4);
+            }
+            const uint2 z = make_uint2(0, 0);  // zero rows for this half chunk
+            for (int pl = 0; pl < po.nsplit; ++pl) {
+              if (po.pad_front && po.m < UM_PADL) *reinterpret_cast<uint2*>(po.at(pl, co0 >> 3, po.m) + (co0 & 7) * 2) = z;
+              if (po.pad_tail && po.m < UM_TAIL) *reinterpret_cast<uint2*>(po.at(pl, co0 >> 3, po.tail_row0 + po.m) + (co0 & 7) * 2) = z;
             }
           }
         }
       } else if (p.epi == EPI_GATE) {
         float* __restrict__ yb = p.y + (size_t)b * p.y_bs + t;
+        float o16[16];
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
-          if (j < jmax) {
-            const float a = acc[j] + s_bias[g * 32 + j];
-            const float gt = acc[j + 1] + s_bias[g * 32 + j + 1];
-            yb[(size_t)((nb + j) >> 1) * p.y_ld] = tanhf(a) * (1.f / (1.f + expf(-gt)));
-          }
+          const float a = acc[j] + s_bias[g * 32 + j];
+          const float gt = acc[j + 1] + s_bias[g * 32 + j + 1];
+          const float v = tanhf(a) * (1.f / (1.f + expf(-gt)));
+          o16[j >> 1] = (t_ok && j < jmax) ? v : 0.f;
+        }
+        if (t_ok && p.y) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (2 * j < jmax) yb[(size_t)((nb >> 1) + j) * p.y_ld] = o16[j];
+        }
+        if (po.base) {
+#pragma unroll
+          for (int q = 0; q < 2; ++q)
+            if (q * 16 < jmax) plane_store8(po, (nb >> 4) + q, (long long)UM_PADL + t, o16 + q * 8);
         }
       } else if (p.epi == EPI_RESSKIP) {
-        float* yb = p.y + (size_t)b * p.y_bs + t;
-        float* ab = p.aux + (size_t)b * p.aux_bs + t;
+        // a 32-channel group lies entirely on one side of `split` (split is a multiple of 32)
+        const bool in_y = nb < p.split;
+        float* db = in_y ? p.y + (size_t)b * p.y_bs + (size_t)nb * p.y_ld + t
+                         : p.aux + (size_t)b * p.aux_bs + (size_t)(nb - p.split) * p.aux_ld + t;
+        const int ld = in_y ? p.y_ld : p.aux_ld;
+        const bool load_old = t_ok && (in_y || !p.first);
         float old[32];
+        if (load_old) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {  // branch-free so the 32 loads are in flight together
-          const int co = nb + j;
-          const bool in_y = co < p.split;
-          const bool need = j < jmax && (in_y || !p.first);
-          const float* src = in_y ? yb + (size_t)co * p.y_ld : ab + (size_t)(co - p.split) * p.aux_ld;
-          const float o = *(need ? src : yb);
-          old[j] = need ? o : 0.f;
+          for (int j = 0; j < 32; ++j) old[j] = db[(size_t)(j < jmax ? j : 0) * ld];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) old[j] = 0.f;
         }
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int co = nb + j;
-          if (j < jmax) {
-            const float v = old[j] + (acc[j] + s_bias[g * 32 + j]);
-            if (co < p.split) yb[(size_t)co * p.y_ld] = v;
-            else ab[(size_t)(co - p.split) * p.aux_ld] = v;
-          }
+        for (int j = 0; j < 32; ++j) acc[j] = (t_ok && j < jmax) ? old[j] + (acc[j] + s_bias[g * 32 + j]) : 0.f;
+        if (t_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < jmax) db[(size_t)j * ld] = acc[j];
+        }
+        const PlaneOut& pp = in_y ? po : po2;
+        if (pp.base) {
+          const int c0 = in_y ? nb : nb - p.split;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (q * 8 < jmax) plane_store8(pp, (c0 >> 3) + q, (long long)UM_PADL + t, acc + q * 8);
         }
       } else {  // EPI_COUPLING (+ InvConvNear^-1 + ActNorm^-1), see conv1d.cuh for the channel algebra
         float* sb = p.y + (size_t)b * p.y_bs + t;
+        const float* s0 = t_ok ? sb : p.y;  // safe address for masked rows
         const int half = p.half;
         float xin[32];  // per group of 4 packed channels: x0[2q], x0[2q+1], x1[2q], x1[2q+1]
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          const int i0 = j < jmax ? (nb + j) >> 1 : 0;
-          xin[j + 0] = sb[(size_t)i0 * p.y_ld];
-          xin[j + 1] = sb[(size_t)(i0 + 1) * p.y_ld];
-          xin[j + 2] = sb[(size_t)(half + i0) * p.y_ld];
-          xin[j + 3] = sb[(size_t)(half + i0 + 1) * p.y_ld];
+          const int i0 = (t_ok && j < jmax) ? (nb + j) >> 1 : 0;
+          xin[j + 0] = s0[(size_t)i0 * p.y_ld];
+          xin[j + 1] = s0[(size_t)(i0 + 1) * p.y_ld];
+          xin[j + 2] = s0[(size_t)(half + i0) * p.y_ld];
+          xin[j + 3] = s0[(size_t)(half + i0 + 1) * p.y_ld];
         }
         float wi[16];
 #pragma unroll
         for (int o = 0; o < 16; ++o) wi[o] = s_inv[o];
+        float zo[32];  // [j..j+3] = new state channels (2q, 2q+1, half+2q, half+2q+1)
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          if (j < jmax) {
-            const int co = nb + j;
-            const int i0 = co >> 1;
-            const int ch[4] = {i0, i0 + 1, half + i0, half + i0 + 1};
-            float vin[4];
-            vin[0] = xin[j + 0];
-            vin[1] = xin[j + 1];
-            vin[2] = (xin[j + 2] - (acc[j] + s_bias[g * 32 + j])) * expf(-(acc[j + 1] + s_bias[g * 32 + j + 1]));
-            vin[3] = (xin[j + 3] - (acc[j + 2] + s_bias[g * 32 + j + 2])) * expf(-(acc[j + 3] + s_bias[g * 32 + j + 3]));
+          const int i0 = (j < jmax) ? (nb + j) >> 1 : 0;
+          const int ch[4] = {i0, i0 + 1, half + i0, half + i0 + 1};
+          float vin[4];
+          vin[0] = xin[j + 0];
+          vin[1] = xin[j + 1];
+          vin[2] = (xin[j + 2] - (acc[j] + s_bias[g * 32 + j])) * expf(-(acc[j + 1] + s_bias[g * 32 + j + 1]));
+          vin[3] = (xin[j + 3] - (acc[j + 2] + s_bias[g * 32 + j + 2])) * expf(-(acc[j + 3] + s_bias[g * 32 + j + 3]));
 #pragma unroll
-            for (int o = 0; o < 4; ++o) {
-              float z = wi[o * 4 + 0] * vin[0];
-              z = fmaf(wi[o * 4 + 1], vin[1], z);
-              z = fmaf(wi[o * 4 + 2], vin[2], z);
-              z = fmaf(wi[o * 4 + 3], vin[3], z);
-              sb[(size_t)ch[o] * p.y_ld] = (z - s_anb[ch[o]]) * s_ans[ch[o]];
+          for (int o = 0; o < 4; ++o) {
+            float z = wi[o * 4 + 0] * vin[0];
+            z = fmaf(wi[o * 4 + 1], vin[1], z);
+            z = fmaf(wi[o * 4 + 2], vin[2], z);
+            z = fmaf(wi[o * 4 + 3], vin[3], z);
+            z = (z - s_anb[ch[o]]) * s_ans[ch[o]];
+            zo[j + o] = (t_ok && j < jmax) ? z : 0.f;
+          }
+        }
+        if (t_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (j < jmax) {
+              const int i0 = (nb + j) >> 1;
+              sb[(size_t)i0 * p.y_ld] = zo[j];
+              sb[(size_t)(i0 + 1) * p.y_ld] = zo[j + 1];
+              sb[(size_t)(half + i0) * p.y_ld] = zo[j + 2];
+              sb[(size_t)(half + i0 + 1) * p.y_ld] = zo[j + 3];
             }
           }
+        }
+        if (po.base) {
+          // 32 packed columns = 8 q's = state channels [nb/2, nb/2+16) of both halves: 2 chunks each
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+            for (int q2 = 0; q2 < 2; ++q2) {
+              if (q2 * 16 >= jmax) continue;
+              float v8[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const int i = q2 * 8 + e;  // channel offset inside the 16-channel run
+                v8[e] = zo[(i >> 1) * 4 + hh * 2 + (i & 1)];
+              }
+              plane_store8(po, ((hh * half + (nb >> 1)) >> 3) + q2, (long long)UM_PADL + t, v8);
+            }
         }
       }
     }
@@ -419,7 +629,7 @@ __global__ void __launch_bounds__(UM_NT_THREADS, MT == 1 ? 2 : 1) conv_umma_kern
   if (tid == 0) UM_TRACE(7);
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem, tmem_cols);
+  if (warp == W_MMA) tmem_dealloc(tmem, tmem_cols);
   if (tid == 0) UM_TRACE(8);
 }
 

@@ -254,6 +254,31 @@ struct Timer {
   }
 };
 
+// bf16 plane image of an activation tensor (conv_umma.cuh): [nsplit][kc][rows][8] per batch item
+struct Planes {
+  void* ptr = nullptr;
+  long long bs = 0;  // bytes per batch item
+  int kc = 0, rows = 0, nsplit = 2;
+};
+static int plane_rows(int Lin_max, int u) { return 40 + (Lin_max + 255) / 256 * 256 * u + 256; }
+static size_t plane_item_bytes(int channels, int rows, int nsplit) { return (size_t)nsplit * ((channels + 31) / 32 * 4) * rows * 16; }
+static Planes take_planes(Arena& a, int batch, int channels, int rows, int nsplit) {
+  Planes pl;
+  pl.kc = (channels + 31) / 32 * 4;
+  pl.rows = rows;
+  pl.nsplit = nsplit;
+  pl.bs = (long long)plane_item_bytes(channels, rows, nsplit);
+  pl.ptr = a.take<unsigned char>((size_t)batch * pl.bs);
+  return pl;
+}
+static void set_in(ConvParams& p, const Planes& pl) {
+  p.xp = pl.ptr; p.xp_bs = pl.bs; p.xp_kc = pl.kc; p.xp_rows = pl.rows;
+}
+static void set_out(ConvParams& p, const Planes& pl, float slope, const Planes* second = nullptr) {
+  p.yp = pl.ptr; p.yp_bs = pl.bs; p.yp_kc = pl.kc; p.yp_rows = pl.rows; p.yp_nsplit = pl.nsplit; p.yp_slope = slope;
+  if (second) p.yp2 = second->ptr;
+}
+
 static int g_conv_mode = -1;  // 0 = fp32 SIMT everywhere, 1 = tcgen05 where a weight image exists
 static bool use_umma() {
   if (g_conv_mode < 0) {
@@ -294,6 +319,7 @@ static void conv(b200tts_call* c, ConvParams& p, const ConvW& w, int batch, int 
     c->launches += launch_conv_umma(p, batch, Lmax, s);
   } else {
     B2_CHECK(w.w != nullptr, "layer has no fp32 weights for the SIMT path");
+    B2_CHECK(p.y != nullptr || p.epi == EPI_COUPLING, "SIMT path needs an fp32 output buffer");
     c->launches += launch_conv1d(p, batch, Lmax, s);
   }
 }
@@ -493,6 +519,9 @@ static void glow_flow_impl(const b200tts_glow* m, b200tts_call* c, float noise_s
   c->idx_ld = round_up(std::max(Ty, 1), 32);
   const bool eps_host = eps && !is_device_ptr(eps);
   size_t need = Arena::pad(B * c->idx_ld, 4) + Arena::pad((size_t)B * C * ldq, 4) + 3 * Arena::pad((size_t)B * Hd * ldq, 4);
+  const int prow = plane_rows(Tq, 1);
+  const bool um = use_umma() && C % 32 == 0 && Hd % 32 == 0;  // plane images hold whole 32-channel chunks
+  if (um) need += Arena::pad(B * plane_item_bytes(C, prow, 2), 1) + 3 * Arena::pad(B * plane_item_bytes(Hd, prow, 2), 1);
   if (eps_host) need += Arena::pad((size_t)B * mel * eps_ld, 4);
   if (c->debug) need += Arena::pad((size_t)m->n_blocks * B * C * ldq, 4);
   c->dec.reserve(need + extra_bytes + 4096);
@@ -501,6 +530,13 @@ static void glow_flow_impl(const b200tts_glow* m, b200tts_call* c, float noise_s
   float* Hh = c->dec.take<float>((size_t)B * Hd * ldq);
   float* ACT = c->dec.take<float>((size_t)B * Hd * ldq);
   float* SK = c->dec.take<float>((size_t)B * Hd * ldq);
+  Planes S_p, H_p, A_p, K_p;  // bf16 operand images of the flow state, WN hidden state, gate output, skip sum
+  if (um) {
+    S_p = take_planes(c->dec, batch, C, prow, 2);
+    H_p = take_planes(c->dec, batch, Hd, prow, 2);
+    A_p = take_planes(c->dec, batch, Hd, prow, 2);
+    K_p = take_planes(c->dec, batch, Hd, prow, 2);
+  }
   const float* eps_d = eps;
   if (eps_host) {
     B2_CHECK(eps_ld >= Ty, "eps_ld smaller than the longest item");
@@ -530,21 +566,38 @@ static void glow_flow_impl(const b200tts_glow* m, b200tts_call* c, float noise_s
     const GlowFlow& f = m->flow[blk];
     // CouplingBlock reverse                                     attentions.py:119-142
     ConvParams p = mk(S, C, Hh, Hd);  // start reads x0 = state[:, :C/2]
+    if (um) {
+      if (blk != m->n_blocks - 1) set_in(p, S_p);  // the first state comes from the expand kernel (fp32 gather)
+      set_out(p, H_p, 1.f);
+    }
     conv(c, p, f.start, batch, Tq, s);
     for (int l = 0; l < m->n_block_layers; ++l) {  // WN       layers.py:138-162
       int dil = 1;
       for (int j = 0; j < l; ++j) dil *= m->dil_rate;
       p = mk(Hh, Hd, ACT, Hd);
       p.dil = dil; p.pad_left = (m->kd * dil - dil) / 2; p.epi = EPI_GATE;
+      if (um && f.in[l].wu) {
+        set_in(p, H_p);
+        set_out(p, A_p, 1.f);
+        p.y = nullptr;  // the gate output is only ever read as an MMA operand
+      }
       conv(c, p, f.in[l], batch, Tq, s);
       p = mk(ACT, Hd, Hh, Hd);
       p.epi = EPI_RESSKIP; p.aux = SK; p.aux_bs = (long long)Hd * ldq; p.aux_ld = ldq;
       p.split = l < m->n_block_layers - 1 ? Hd : 0;
       p.first = l == 0;
+      if (um && f.rs[l].wu) {
+        set_in(p, A_p);
+        set_out(p, H_p, 1.f, &K_p);
+      }
       conv(c, p, f.rs[l], batch, Tq, s);
     }
     p = mk(SK, Hd, S, C);
     p.epi = EPI_COUPLING; p.inv_w = f.inv; p.an_bias = f.an_bias; p.an_scale = f.an_scale; p.half = C / 2;
+    if (um && f.end.wu) {
+      set_in(p, K_p);
+      set_out(p, S_p, 1.f);
+    }
     conv(c, p, f.end, batch, Tq, s);
     if (c->taps_d)
       B2_CUDA(cudaMemcpyAsync(c->taps_d + (size_t)blk * B * C * ldq, S, sizeof(float) * B * C * ldq,
@@ -652,12 +705,30 @@ static void hifigan_run(const b200tts_hifigan* m, b200tts_call* c, const float* 
   const int Lout_ld = ld0 * hop;
   size_t need = Arena::pad((size_t)B * m->C0 * ld0, 4) + 14 * Arena::pad(B * stage_max, 4) +
                 Arena::pad((size_t)B * Lout_ld, 4) + Arena::pad(B, 4) + Arena::pad((size_t)B * Lout_ld, 2);
+  // bf16 operand images: conv_pre output + 7 per stage set (two alternating sets)
+  const bool um = use_umma() && m->conv_pre.wu != nullptr && m->C0 % 32 == 0;
+  size_t plane_max = 0;
+  if (um) {
+    int Lin = Tmax;
+    for (int i = 0; i < m->n_ups; ++i) {
+      plane_max = std::max(plane_max, plane_item_bytes(m->C0 >> (i + 1), plane_rows(Lin, m->up_rate[i]), 2));
+      Lin *= m->up_rate[i];
+    }
+    need += Arena::pad(B * plane_item_bytes(m->C0, plane_rows(Tmax, 1), 2), 1) + 14 * Arena::pad(B * plane_max, 1);
+  }
   c->voc.reserve(need + 4096);
   float* P = c->voc.take<float>((size_t)B * m->C0 * ld0);
   float* setb[2][7];
   for (int a = 0; a < 2; ++a)
     for (int j = 0; j < 7; ++j) setb[a][j] = c->voc.take<float>(B * stage_max);
   float* pcm_d = c->voc.take<float>((size_t)B * Lout_ld);
+  Planes P_p;
+  unsigned char* pset[2][7] = {};
+  if (um) {
+    P_p = take_planes(c->voc, batch, m->C0, plane_rows(Tmax, 1), 2);
+    for (int a = 0; a < 2; ++a)
+      for (int j = 0; j < 7; ++j) pset[a][j] = c->voc.take<unsigned char>(B * plane_max);
+  }
   unsigned int* peak_d = c->voc.take<unsigned int>(B);
   short* i16_d = c->voc.take<short>((size_t)B * Lout_ld);
 
@@ -669,6 +740,7 @@ static void hifigan_run(const b200tts_hifigan* m, b200tts_call* c, const float* 
       p.x = mel_d; p.x_bs = (long long)m->mel * mel_ld; p.x_ld = mel_ld;
       p.y = P; p.y_bs = (long long)m->C0 * ld0; p.y_ld = ld0;
       p.lens = frames_d; p.len_mul = 1; p.Lin = Tmax; p.pad_left = 3;
+      if (um) set_out(p, P_p, 0.1f);  // ups[0] consumes leaky_relu(conv_pre(x), 0.1)
       conv(c, p, m->conv_pre, batch, Tmax, s);
     }
     const float *in1 = P, *in2 = nullptr, *in3 = nullptr;
@@ -679,6 +751,27 @@ static void hifigan_run(const b200tts_hifigan* m, b200tts_call* c, const float* 
       const int Lld = Lin_ld * u;
       float** bs_ = setb[i & 1];
       float* U = bs_[0];
+      // operand images of this stage: U, R[3], T[3] (leaky_relu(.,0.1) already applied: every consumer wants it)
+      Planes U_p, R_p[3], T_p[3];
+      const int Lin_max = Tmax * len_mul;
+      // images hold whole 32-channel chunks: narrower stages (vctk_medium tail) stay on the fp32 gather path
+      const bool ump = um && cout % 32 == 0;
+      if (ump) {
+        auto mkp = [&](unsigned char* ptr) {
+          Planes pl;
+          pl.kc = (cout + 31) / 32 * 4;
+          pl.rows = plane_rows(Lin_max, u);
+          pl.nsplit = 2;
+          pl.bs = (long long)plane_item_bytes(cout, pl.rows, 2);
+          pl.ptr = ptr;
+          return pl;
+        };
+        U_p = mkp(pset[i & 1][0]);
+        for (int j = 0; j < 3; ++j) {
+          R_p[j] = mkp(pset[i & 1][1 + j]);
+          T_p[j] = mkp(pset[i & 1][4 + j]);
+        }
+      }
       // x = leaky_relu(x, 0.1); x = ups[i](x)                    hifi_gan/models.py:189-190
       {
         ConvParams p;
@@ -689,6 +782,8 @@ static void hifigan_run(const b200tts_hifigan* m, b200tts_call* c, const float* 
         p.lens = frames_d; p.len_mul = len_mul; p.Lin = Tmax * len_mul;
         if (m->ups_ps[i].wu && use_umma()) {
           p.pix = u; p.pad_left = 1;  // one 3-tap conv, cout*u pixel-shuffled channels
+          if (um && i == 0) set_in(p, P_p);  // later stages read the MRF mean of three tensors (fp32 gather)
+          if (ump) set_out(p, U_p, 0.1f);
           conv(c, p, m->ups_ps[i], batch, Tmax * len_mul, s);
         } else {
           p.n_phase = u; p.tpad = (m->up_k[i] - u) / 2;
@@ -714,6 +809,12 @@ static void hifigan_run(const b200tts_hifigan* m, b200tts_call* c, const float* 
           p.dil = r.dil[d]; p.pad_left = (r.k * r.dil[d] - r.dil[d]) / 2;
           if (m->resblock == 1) {
             p.y = T; p.y_bs = (long long)cout * Lld; p.y_ld = Lld;
+            const bool pl = ump && r.c1[d].wu && r.c2[d].wu;
+            if (pl) {
+              set_in(p, d == 0 ? U_p : R_p[j]);
+              set_out(p, T_p[j], 0.1f);
+              p.y = nullptr;  // T is only ever read as an MMA operand
+            }
             conv(c, p, r.c1[d], batch, L, sj);
             ConvParams q;
             q.x = T; q.x_bs = (long long)cout * Lld; q.x_ld = Lld;
@@ -722,6 +823,10 @@ static void hifigan_run(const b200tts_hifigan* m, b200tts_call* c, const float* 
             q.dil = 1; q.pad_left = (r.k - 1) / 2;
             q.y = R; q.y_bs = (long long)cout * Lld; q.y_ld = Lld;
             q.res = xin; q.res_bs = (long long)cout * Lld; q.res_ld = Lld;
+            if (pl) {
+              set_in(q, T_p[j]);
+              if (d + 1 < r.ndil) set_out(q, R_p[j], 0.1f);
+            }
             conv(c, q, r.c2[d], batch, L, sj);
           } else {  // ResBlock2                                   hifi_gan/models.py:137-142
             float* dst = (d & 1) ? R : T;  // ping-pong: conv input and output must differ

@@ -107,14 +107,38 @@ __device__ __forceinline__ void plane_store8(const PlaneOut& po, int kc, long lo
   float w[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) w[e] = v8[e] > 0.f ? v8[e] : v8[e] * po.slope;
-  uint4 q[3];
-  if (po.nsplit == 3) split8<3>(w, q);
-  else split8<2>(w, q);
+  const size_t pstride = (size_t)po.kc_total * po.rows * 16;  // bytes between split planes
+  unsigned char* base = po.base + ((size_t)kc * po.rows) * 16;
   const uint4 z = make_uint4(0, 0, 0, 0);
-  for (int pl = 0; pl < po.nsplit; ++pl) {
-    *reinterpret_cast<uint4*>(po.at(pl, kc, row)) = q[pl];
-    if (po.pad_front && po.m < UM_PADL) *reinterpret_cast<uint4*>(po.at(pl, kc, po.m)) = z;
-    if (po.pad_tail && po.m < UM_TAIL) *reinterpret_cast<uint4*>(po.at(pl, kc, po.tail_row0 + po.m)) = z;
+  const bool zf = po.pad_front && po.m < UM_PADL, zt = po.pad_tail && po.m < UM_TAIL;
+  uint4 q[3];
+  if (po.nsplit == 3) {  // straight-line code per split count: no dynamically indexed local arrays
+    split8<3>(w, q);
+    *reinterpret_cast<uint4*>(base + row * 16) = q[0];
+    *reinterpret_cast<uint4*>(base + pstride + row * 16) = q[1];
+    *reinterpret_cast<uint4*>(base + 2 * pstride + row * 16) = q[2];
+    if (zf) {
+      *reinterpret_cast<uint4*>(base + (size_t)po.m * 16) = z;
+      *reinterpret_cast<uint4*>(base + pstride + (size_t)po.m * 16) = z;
+      *reinterpret_cast<uint4*>(base + 2 * pstride + (size_t)po.m * 16) = z;
+    }
+    if (zt) {
+      *reinterpret_cast<uint4*>(base + (po.tail_row0 + po.m) * 16) = z;
+      *reinterpret_cast<uint4*>(base + pstride + (po.tail_row0 + po.m) * 16) = z;
+      *reinterpret_cast<uint4*>(base + 2 * pstride + (po.tail_row0 + po.m) * 16) = z;
+    }
+  } else {
+    split8<2>(w, q);
+    *reinterpret_cast<uint4*>(base + row * 16) = q[0];
+    *reinterpret_cast<uint4*>(base + pstride + row * 16) = q[1];
+    if (zf) {
+      *reinterpret_cast<uint4*>(base + (size_t)po.m * 16) = z;
+      *reinterpret_cast<uint4*>(base + pstride + (size_t)po.m * 16) = z;
+    }
+    if (zt) {
+      *reinterpret_cast<uint4*>(base + (po.tail_row0 + po.m) * 16) = z;
+      *reinterpret_cast<uint4*>(base + pstride + (po.tail_row0 + po.m) * 16) = z;
+    }
   }
 }
 // store 4 consecutive channels (8 bytes at byte offset `boff` inside the 16-byte chunk); no zero-row duty
@@ -227,50 +251,58 @@ __global__ void __launch_bounds__(EW * 32 + 64, (MT == 1 && EW == 8) ? 2 : 1) co
     }
   } else if (warp == W_MMA) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    {
+      // The whole warp runs this loop with uniform control flow so the descriptor arithmetic lives in uniform
+      // registers (UTCHMMA takes its operands from the uniform register file); only lane 0 issues.
       const uint32_t idesc = make_idesc_bf16_f32(128, NT);
-      const uint32_t sA_u = smem_u32(sA), sW_u = smem_u32(sW);
+      // Descriptors differ only in the 14-bit start-address field (bytes >> 4): build them once and add offsets.
+      const uint64_t a_desc0 = make_smem_desc(smem_u32(sA), RA * 16, 128);
+      const uint64_t b_desc0 = make_smem_desc(smem_u32(sW), NT * 16, 128);
+      const uint32_t a_ks = (2 * RA * 16) >> 4, b_ks = (2 * NT * 16) >> 4;  // next K=16 step
+      const uint32_t a_sp = a_split_bytes >> 4, b_sp = w_split_bytes >> 4;  // next split plane
+      const uint32_t a_mt = (128 * 16) >> 4;                                // next 128-row tile
       int n = 0;
       for (int c = 0; c < nch; ++c) {
         const int as = c & 1;
         mbar_wait(&a_full[as], (c >> 1) & 1);
         tc_fence_after();
-        if (c == 0) UM_TRACE(3);
+        if (c == 0 && lane == 0) UM_TRACE(3);
+        const uint64_t a_c = a_desc0 + ((as * a_stage) >> 4);
         for (int k = 0; k < K; ++k, ++n) {
           const int s = n % UM_WSTAGES;
           mbar_wait(&w_full[s], (n / UM_WSTAGES) & 1);
           tc_fence_after();
+          const uint64_t a_k = a_c + (uint32_t)(k * dil);  // conv tap: shift the image by k*dil rows of 16 B
+          const uint64_t b_k = b_desc0 + ((s * w_stage) >> 4);
+          const uint32_t first = (c == 0 && k == 0) ? 0u : 1u;
+          if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < UM_BKC / 16; ++ks) {
-            const uint32_t wb = sW_u + s * w_stage + (2 * ks) * NT * 16;
-            uint64_t bd[NSPLIT];
+            for (int ks = 0; ks < UM_BKC / 16; ++ks) {
 #pragma unroll
-            for (int sp = 0; sp < NSPLIT; ++sp) bd[sp] = make_smem_desc(wb + sp * w_split_bytes, NT * 16, 128);
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-              const uint32_t ab = sA_u + as * a_stage + (2 * ks) * RA * 16 + (mt * 128 + k * dil) * 16;
-              uint64_t ad[NSPLIT];
-#pragma unroll
-              for (int sp = 0; sp < NSPLIT; ++sp) ad[sp] = make_smem_desc(ab + sp * a_split_bytes, RA * 16, 128);
-              const uint32_t d0 = tmem + (0 * MT + mt) * NT, d1 = tmem + (1 * MT + mt) * NT;
-              const uint32_t first = (c == 0 && k == 0 && ks == 0) ? 0u : 1u;
-              mma_bf16_ss(d0, ad[0], bd[0], idesc, first);   // hi*hi
-              mma_bf16_ss(d1, ad[0], bd[1], idesc, first);   // hi*lo
-              mma_bf16_ss(d1, ad[1], bd[0], idesc, 1u);      // lo*hi
-              if (NSPLIT == 3) {
-                const uint32_t d2 = tmem + (2 * MT + mt) * NT;
-                mma_bf16_ss(d2, ad[1], bd[1], idesc, first); // lo*lo
-                mma_bf16_ss(d2, ad[0], bd[2], idesc, 1u);    // hi*lo2
-                mma_bf16_ss(d2, ad[2], bd[0], idesc, 1u);    // lo2*hi
+              for (int mt = 0; mt < MT; ++mt) {
+                const uint64_t a0 = a_k + ks * a_ks + mt * a_mt, b0 = b_k + ks * b_ks;
+                const uint32_t acc0 = ks == 0 ? first : 1u;
+                const uint32_t d0 = tmem + (0 * MT + mt) * NT, d1 = tmem + (1 * MT + mt) * NT;
+                mma_bf16_ss(d0, a0, b0, idesc, acc0);                // hi*hi
+                mma_bf16_ss(d1, a0, b0 + b_sp, idesc, acc0);         // hi*lo
+                mma_bf16_ss(d1, a0 + a_sp, b0, idesc, 1u);           // lo*hi
+                if (NSPLIT == 3) {
+                  const uint32_t d2 = tmem + (2 * MT + mt) * NT;
+                  mma_bf16_ss(d2, a0 + a_sp, b0 + b_sp, idesc, acc0);  // lo*lo
+                  mma_bf16_ss(d2, a0, b0 + 2 * b_sp, idesc, 1u);       // hi*lo2
+                  mma_bf16_ss(d2, a0 + 2 * a_sp, b0, idesc, 1u);       // lo2*hi
+                }
               }
             }
+            mma_commit(&w_empty[s]);  // frees the weight stage when these MMAs have completed
           }
-          mma_commit(&w_empty[s]);  // frees the weight stage when these MMAs have completed
+          __syncwarp();
         }
-        mma_commit(&a_empty[as]);   // frees the activation stage
+        if (elect_one()) mma_commit(&a_empty[as]);  // frees the activation stage
+        __syncwarp();
       }
-      mma_commit(acc_full);
-      UM_TRACE(4);
+      if (elect_one()) mma_commit(acc_full);
+      if (lane == 0) UM_TRACE(4);
     }
   } else {
     if (planes_in) {
@@ -409,6 +441,7 @@ __global__ void __launch_bounds__(EW * 32 + 64, (MT == 1 && EW == 8) ? 2 : 1) co
       const int nb = n0 + g * 32;  // packed channel of acc[0]
       const int jmax = min(32, min(NT - g * 32, p.Cout - nb));
       if (jmax <= 0) continue;
+      if (tid == 0 && g == cset) UM_TRACE(9);
       if (p.epi == EPI_PLAIN && u == 1) {
         float* __restrict__ yb = p.y + (size_t)b * p.y_bs + t;
         float rv[32];
@@ -517,7 +550,11 @@ __global__ void __launch_bounds__(EW * 32 + 64, (MT == 1 && EW == 8) ? 2 : 1) co
         for (int j = 0; j < 32; j += 2) {
           const float a = acc[j] + s_bias[g * 32 + j];
           const float gt = acc[j + 1] + s_bias[g * 32 + j + 1];
-          const float v = tanhf(a) * (1.f / (1.f + expf(-gt)));
+          // tanh(a) = 1 - 2/(e^{2a}+1), sigmoid(g) = 1/(1+e^{-g}) with ex2.approx / fast division (~2 ulp each):
+          // absolute error ~1e-7, far inside the bf16-split error budget of this path
+          const float th = 1.f - __fdividef(2.f, __expf(2.f * a) + 1.f);
+          const float sg = __fdividef(1.f, 1.f + __expf(-gt));
+          const float v = th * sg;
           o16[j >> 1] = (t_ok && j < jmax) ? v : 0.f;
         }
         if (t_ok && p.y) {
@@ -547,11 +584,13 @@ __global__ void __launch_bounds__(EW * 32 + 64, (MT == 1 && EW == 8) ? 2 : 1) co
         }
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc[j] = (t_ok && j < jmax) ? old[j] + (acc[j] + s_bias[g * 32 + j]) : 0.f;
+        if (tid == 0 && g == cset) UM_TRACE(10);
         if (t_ok) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (j < jmax) db[(size_t)j * ld] = acc[j];
         }
+        if (tid == 0 && g == cset) UM_TRACE(11);
         const PlaneOut& pp = in_y ? po : po2;
         if (pp.base) {
           const int c0 = in_y ? nb : nb - p.split;
@@ -583,8 +622,8 @@ __global__ void __launch_bounds__(EW * 32 + 64, (MT == 1 && EW == 8) ? 2 : 1) co
           float vin[4];
           vin[0] = xin[j + 0];
           vin[1] = xin[j + 1];
-          vin[2] = (xin[j + 2] - (acc[j] + s_bias[g * 32 + j])) * expf(-(acc[j + 1] + s_bias[g * 32 + j + 1]));
-          vin[3] = (xin[j + 3] - (acc[j + 2] + s_bias[g * 32 + j + 2])) * expf(-(acc[j + 3] + s_bias[g * 32 + j + 3]));
+          vin[2] = (xin[j + 2] - (acc[j] + s_bias[g * 32 + j])) * __expf(-(acc[j + 1] + s_bias[g * 32 + j + 1]));
+          vin[3] = (xin[j + 3] - (acc[j + 2] + s_bias[g * 32 + j + 2])) * __expf(-(acc[j + 3] + s_bias[g * 32 + j + 3]));
 #pragma unroll
           for (int o = 0; o < 4; ++o) {
             float z = wi[o * 4 + 0] * vin[0];

@@ -309,10 +309,11 @@ static void conv(b200tts_call* c, ConvParams& p, const ConvW& w, int batch, int 
       p.dbg = dbg;
       c->launches += launch_conv_umma(p, batch, Lmax, s);
       B2_CUDA(cudaDeviceSynchronize());
-      fprintf(stderr, "[conv] Cin %4d Cout %4d K %2d L %6d nt %3d | gap %6.1f prologue %5.1f A0 %5.1f mma0 %5.1f issued %6.1f Alast %6.1f acc %6.1f epi %5.1f end %5.1f | total %6.1f us\n",
+      fprintf(stderr, "[conv] Cin %4d Cout %4d K %2d L %6d nt %3d | gap %6.1f prologue %5.1f A0 %5.1f mma0 %5.1f issued %6.1f Alast %6.1f acc %6.1f epi %5.1f end %5.1f | total %6.1f us | epi: ld %4.1f math %4.1f st %4.1f\n",
               p.Cin, p.Cout, p.K, Lmax, p.um_nt, last_end ? (dbg[0] - last_end) * 1e-3 : 0.0, (dbg[1] - dbg[0]) * 1e-3, (dbg[2] - dbg[1]) * 1e-3,
               (dbg[3] - dbg[1]) * 1e-3, (dbg[4] - dbg[1]) * 1e-3, (dbg[5] - dbg[1]) * 1e-3, (dbg[6] - dbg[1]) * 1e-3, (dbg[7] - dbg[6]) * 1e-3,
-              (dbg[8] - dbg[7]) * 1e-3, (dbg[8] - dbg[0]) * 1e-3);
+              (dbg[8] - dbg[7]) * 1e-3, (dbg[8] - dbg[0]) * 1e-3, dbg[9] ? (dbg[9] - dbg[6]) * 1e-3 : 0.0,
+              dbg[10] ? (dbg[10] - dbg[9]) * 1e-3 : 0.0, dbg[11] ? (dbg[11] - dbg[10]) * 1e-3 : 0.0);
       last_end = dbg[8];
       return;
     }

@@ -91,12 +91,12 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 #pragma unroll
   for (int i = 0; i < LN_MAXC / 8; ++i) {
     const int c = ty + i * 8;
-    float a = 0.f;
-    if (valid && c < C) {
-      a = xb[(size_t)c * ld + t];
-      if (rb) a += rb[(size_t)c * ld + t];
-      if (pre_relu) a = fmaxf(a, 0.f);
-    }
+    const bool ok = valid && c < C;  // branch-free: all loads of the column are in flight together
+    const size_t off = ok ? (size_t)c * ld + t : 0;
+    float a = xb[off];
+    if (rb) a += rb[off];
+    if (pre_relu) a = fmaxf(a, 0.f);
+    a = ok ? a : 0.f;
     v[i] = a;
     s += a;
   }

@@ -93,4 +93,12 @@ struct ConvParams {
   float yp_slope = 1.f;  // planes hold v > 0 ? v : v*slope (the consumer's LeakyReLU); 1 = identity
 };
 
+// up to three independent convs of identical output geometry in ONE launch (the three MRF ResBlock branches of a
+// HiFi-GAN stage: same C and L, different kernel size / dilation / weights / buffers); blockIdx.z = branch*zb + item
+struct ConvBatch {
+  int n = 1;
+  int zb = 1;  // batch items per branch
+  ConvParams p[3];
+};
+
 }  // namespace b2

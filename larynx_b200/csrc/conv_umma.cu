@@ -1,4 +1,6 @@
 // conv_umma.cu — launcher of the tcgen05 implicit-GEMM conv (conv_umma.cuh).
+#include <stdlib.h>
+
 #include "conv_umma.cuh"
 #include "kernels.cuh"
 
@@ -17,35 +19,68 @@ void conv_umma_init_attributes() {
 }
 
 template <int MT, int NSPLIT, int EW, int WST>
-static void launch_umma_cfg(const ConvParams& p, int batch, int Lmax, cudaStream_t s) {
+static void launch_umma_cfg(const ConvBatch& pb, int batch, int Lmax, cudaStream_t s) {
+  const ConvParams& p = pb.p[0];
   const size_t smem = UmmaCfg<MT>::smem_bytes(NSPLIT, p.um_nt, WST);
   B2_CHECK(smem <= 227 * 1024, "conv_umma: shared memory budget exceeded");
   const int ntiles = (p.Cout + p.um_nt - 1) / p.um_nt;
-  dim3 grid((Lmax + MT * 128 - 1) / (MT * 128), ntiles, batch);
-  conv_umma_kernel<MT, NSPLIT, EW, WST><<<grid, EW * 32 + 64, smem, s>>>(p);
+  dim3 grid((Lmax + MT * 128 - 1) / (MT * 128), ntiles, batch * pb.n);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(EW * 32 + 64);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // PDL: overlap our prologue with the previous kernel
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  B2_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<MT, NSPLIT, EW, WST>, pb));
 }
 
-int launch_conv_umma(const ConvParams& p, int batch, int Lmax, cudaStream_t stream) {
-  B2_CHECK(p.wu != nullptr && p.um_nt >= 16 && p.um_nt <= 128 && p.um_nt % 16 == 0, "conv_umma: bad weight image");
-  B2_CHECK((p.K - 1) * p.dil <= UM_HALO, "conv_umma: receptive field too wide");
-  B2_CHECK(p.pad_left <= UM_PADL, "conv_umma: left padding too wide");
-  B2_CHECK(p.n_phase == 1, "conv_umma: transposed convs are packed as pixel-shuffle convs");
-  if (p.xp) B2_CHECK(p.xp_kc >= (p.Cin + 31) / 32 * 4, "conv_umma: input plane image too narrow");
+int launch_conv_umma_batch(const ConvParams* ps, int n, int batch, int Lmax, cudaStream_t stream) {
+  B2_CHECK(n >= 1 && n <= 3, "conv_umma: 1..3 convs per launch");
+  ConvBatch pb;
+  pb.n = n;
+  pb.zb = batch;
+  for (int i = 0; i < n; ++i) {
+    const ConvParams& p = ps[i];
+    B2_CHECK(p.wu != nullptr && p.um_nt >= 16 && p.um_nt <= 128 && p.um_nt % 16 == 0, "conv_umma: bad weight image");
+    B2_CHECK((p.K - 1) * p.dil <= UM_HALO, "conv_umma: receptive field too wide");
+    B2_CHECK(p.pad_left <= UM_PADL, "conv_umma: left padding too wide");
+    B2_CHECK(p.n_phase == 1, "conv_umma: transposed convs are packed as pixel-shuffle convs");
+    if (p.xp) B2_CHECK(p.xp_kc >= (p.Cin + 31) / 32 * 4, "conv_umma: input plane image too narrow");
+    B2_CHECK(p.Cout == ps[0].Cout && p.um_nt == ps[0].um_nt && p.um_nsplit == ps[0].um_nsplit && p.Cin == ps[0].Cin,
+             "conv_umma: convs of one launch must share their geometry");
+    pb.p[i] = p;
+  }
   if (Lmax <= 0 || batch <= 0) return 0;
+  const ConvParams& p = ps[0];
   const int ntiles = (p.Cout + p.um_nt - 1) / p.um_nt;
-  const long long ctas1 = (long long)((Lmax + 127) / 128) * ntiles * batch;
-  const long long ctas2 = (long long)((Lmax + 255) / 256) * ntiles * batch;
+  const long long ctas1 = (long long)((Lmax + 127) / 128) * ntiles * batch * n;
+  const long long ctas2 = (long long)((Lmax + 255) / 256) * ntiles * batch * n;
+  static long long mt2_min = -1, ew16_max = -1;
+  if (mt2_min < 0) {
+    const char* e1 = getenv("B200TTS_MT2_MIN");
+    const char* e2 = getenv("B200TTS_EW16_MAX");
+    mt2_min = e1 ? atoll(e1) : (1LL << 40);  // measured: two co-resident 128-row CTAs per SM beat one 256-row CTA
+    ew16_max = e2 ? atoll(e2) : 148;
+  }
   if (p.um_nsplit == 3) {
-    launch_umma_cfg<1, 3, 16, 4>(p, batch, Lmax, stream);
-  } else if (ctas2 >= 148) {
-    launch_umma_cfg<2, 2, 8, 6>(p, batch, Lmax, stream);
-  } else if (ctas1 > 148) {
-    launch_umma_cfg<1, 2, 8, 3>(p, batch, Lmax, stream);
+    launch_umma_cfg<1, 3, 16, 4>(pb, batch, Lmax, stream);
+  } else if (ctas2 >= mt2_min) {
+    launch_umma_cfg<2, 2, 8, 6>(pb, batch, Lmax, stream);
+  } else if (ctas1 > ew16_max) {
+    launch_umma_cfg<1, 2, 8, 3>(pb, batch, Lmax, stream);
   } else {
-    launch_umma_cfg<1, 2, 16, 6>(p, batch, Lmax, stream);
+    launch_umma_cfg<1, 2, 16, 6>(pb, batch, Lmax, stream);
   }
   B2_CUDA(cudaGetLastError());
   return 1;
+}
+
+int launch_conv_umma(const ConvParams& p, int batch, int Lmax, cudaStream_t stream) {
+  return launch_conv_umma_batch(&p, 1, batch, Lmax, stream);
 }
 
 }  // namespace b2

@@ -162,8 +162,9 @@ __device__ __forceinline__ void plane_store4(const PlaneOut& po, int kc, int bof
 // WST: weight ring depth.  <1,2,8,3> fits two CTAs per SM (large grids); EW = 16 variants are for small grids
 // where a CTA has the SM to itself and the serial latency of one tile is what matters.
 template <int MT, int NSPLIT, int EW, int WST>
-__global__ void __launch_bounds__(EW * 32 + 64, (MT == 1 && EW == 8) ? 2 : 1) conv_umma_kernel(const ConvParams p) {
+__global__ void __launch_bounds__(EW * 32 + 64, (MT == 1 && EW == 8) ? 2 : 1) conv_umma_kernel(const __grid_constant__ ConvBatch pb) {
   using namespace umma;
+  const ConvParams& p = pb.p[blockIdx.z / pb.zb];
   using C = UmmaCfg<MT>;
   constexpr int RA = C::RA;
   constexpr int UM_WSTAGES = WST;
@@ -195,7 +196,7 @@ __global__ void __launch_bounds__(EW * 32 + 64, (MT == 1 && EW == 8) ? 2 : 1) co
   float* s_ans = s_anb + 256;                           // [2*half]  ActNorm exp(-logs)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.z;
+  const int b = blockIdx.z % pb.zb;
   const int t0 = blockIdx.x * (MT * 128);
   const int ntile = blockIdx.y;
   const int n0 = ntile * NT;
@@ -235,6 +236,9 @@ __global__ void __launch_bounds__(EW * 32 + 64, (MT == 1 && EW == 8) ? 2 : 1) co
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   if (tid == 0) UM_TRACE(1);
+  // Programmatic dependent launch: let the next kernel in the stream start its prologue / weight prefetch now;
+  // it blocks in griddepcontrol.wait before touching anything this grid writes.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == W_LOAD) {
     // ===================== weight producer =====================
@@ -305,6 +309,8 @@ __global__ void __launch_bounds__(EW * 32 + 64, (MT == 1 && EW == 8) ? 2 : 1) co
       if (lane == 0) UM_TRACE(4);
     }
   } else {
+    // everything below reads activations written by the previous grid (weights above are static)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (planes_in) {
       // ===================== A by bulk copy from the producer's plane image =====================
       if (tid == 0) {

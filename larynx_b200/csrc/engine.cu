@@ -384,6 +384,8 @@ static void glow_bind(b200tts_glow* m) {
   }
 }
 
+static const int* lens_for_ln(const b200tts_call* c) { return c->xlen_d; }
+
 static void glow_encode_impl(const b200tts_glow* m, b200tts_call* c, const int64_t* ids, const int32_t* x_len,
                              int batch, int max_tx, float length_scale, int32_t* y_len_out) {
   B2_CHECK(batch > 0 && max_tx > 0, "empty batch");
@@ -399,6 +401,11 @@ static void glow_encode_impl(const b200tts_glow* m, b200tts_call* c, const int64
   const size_t act = (size_t)B * ld;
   need += Arena::pad(act * H, 4) * 4 + Arena::pad(act * 3 * H, 4) + Arena::pad(act * F, 4) +
           Arena::pad(act * Fd, 4) * 2 + Arena::pad(act * mel, 4);
+  // bf16 operand images (3-way split: the encoder feeds the bit-exact alignment) written by LN / conv epilogues
+  const bool um = use_umma() && H % 32 == 0 && F % 32 == 0 && Fd % 32 == 0;
+  const int prow = plane_rows(max_tx, 1);
+  if (um) need += 3 * Arena::pad(B * plane_item_bytes(H, prow, 3), 1) + Arena::pad(B * plane_item_bytes(F, prow, 3), 1) +
+                  Arena::pad(B * plane_item_bytes(Fd, prow, 3), 1);
   c->enc.reserve(need + 4096);
   long long* ids_d = c->enc.take<long long>(B * max_tx);
   c->xlen_d = c->enc.take<int>(B);
@@ -416,6 +423,20 @@ static void glow_encode_impl(const b200tts_glow* m, b200tts_call* c, const int64
   float* D1 = c->enc.take<float>(act * Fd);
   float* D2 = c->enc.take<float>(act * Fd);
   c->xm_d = c->enc.take<float>(act * mel);
+  Planes X_p, P_p[2], FF_p, D1_p;
+  if (um) {
+    X_p = take_planes(c->enc, batch, H, prow, 3);
+    P_p[0] = take_planes(c->enc, batch, H, prow, 3);
+    P_p[1] = take_planes(c->enc, batch, H, prow, 3);
+    FF_p = take_planes(c->enc, batch, F, prow, 3);
+    D1_p = take_planes(c->enc, batch, Fd, prow, 3);
+  }
+  auto ln = [&](const float* x, const float* res, const float* g, const float* bta, float* y, int C, int pre_relu, int post_relu,
+                const Planes* pl) {
+    launch_layernorm(x, res, g, bta, y, (long long)C * ld, ld, C, lens_for_ln(c), batch, max_tx, pre_relu, post_relu, s,
+                     pl ? pl->ptr : nullptr, pl ? pl->bs : 0, pl ? pl->kc : 0, pl ? pl->rows : 0, pl ? pl->nsplit : 3);
+    c->launches++;
+  };
 
   Timer tm(c);
   B2_CUDA(cudaMemcpyAsync(ids_d, ids, sizeof(long long) * B * max_tx, cudaMemcpyDefault, s));
@@ -440,55 +461,66 @@ static void glow_encode_impl(const b200tts_glow* m, b200tts_call* c, const int64
       float* o = bufs[i & 1];
       ConvParams p = mk(h, H, o, H);
       p.pad_left = 2;
+      if (um && i > 0) set_in(p, P_p[(i - 1) & 1]);  // the embedding itself is gathered from fp32
       conv(c, p, m->pre_conv[i], batch, max_tx, s);
-      launch_layernorm(o, nullptr, m->pre_lng[i], m->pre_lnb[i], o, (long long)H * ld, ld, H, lens, batch, max_tx, 0,
-                       1, s);
-      c->launches++;
+      ln(o, nullptr, m->pre_lng[i], m->pre_lnb[i], o, H, 0, 1, um ? &P_p[i & 1] : nullptr);
       h = o;
     }
     ConvParams p = mk(h, H, X, H);
     p.res = X; p.res_bs = (long long)H * ld; p.res_ld = ld;
+    if (um) {
+      set_in(p, P_p[0]);
+      set_out(p, X_p, 1.f);
+    }
     conv(c, p, m->pre_proj, batch, max_tx, s);
   }
   // encoder layers                                              attentions.py:62-74
   for (int i = 0; i < m->n_layers; ++i) {
     const GlowEnc& e = m->enc[i];
     ConvParams p = mk(X, H, QKV, 3 * H);
+    if (um) set_in(p, X_p);
     conv(c, p, e.qkv, batch, max_tx, s);
     launch_rel_attention(QKV, (long long)3 * H * ld, ld, H, m->n_heads, e.rel_k, e.rel_v, m->window, lens, batch,
                          max_tx, ATT, (long long)H * ld, ld, s);
     c->launches++;
     p = mk(ATT, H, A, H);
     conv(c, p, e.o, batch, max_tx, s);
-    launch_layernorm(X, A, e.ln1g, e.ln1b, X, (long long)H * ld, ld, H, lens, batch, max_tx, 0, 0, s);
-    c->launches++;
+    ln(X, A, e.ln1g, e.ln1b, X, H, 0, 0, um ? &X_p : nullptr);
     p = mk(X, H, FF, F);
     p.pad_left = m->K / 2; p.act = ACT_RELU;
+    if (um && e.ffn1.wu && e.ffn2.wu) {
+      set_in(p, X_p);
+      set_out(p, FF_p, 1.f);
+      p.y = nullptr;  // the FFN hidden activation is only ever read as an MMA operand
+    }
     conv(c, p, e.ffn1, batch, max_tx, s);
     p = mk(FF, F, A, H);
     p.pad_left = m->K / 2;
+    if (um && e.ffn1.wu && e.ffn2.wu) set_in(p, FF_p);
     conv(c, p, e.ffn2, batch, max_tx, s);
-    launch_layernorm(X, A, e.ln2g, e.ln2b, X, (long long)H * ld, ld, H, lens, batch, max_tx, 0, 0, s);
-    c->launches++;
+    ln(X, A, e.ln2g, e.ln2b, X, H, 0, 0, um ? &X_p : nullptr);
   }
   // proj_m                                                      models.py:133
   {
     ConvParams p = mk(X, H, c->xm_d, mel);
+    if (um) set_in(p, X_p);
     conv(c, p, m->proj_m, batch, max_tx, s);
   }
   // duration predictor                                          models.py:39-49
   {
     ConvParams p = mk(X, H, D1, Fd);
     p.pad_left = m->K / 2;
+    if (um) set_in(p, X_p);
     conv(c, p, m->dp1, batch, max_tx, s);
-    launch_layernorm(D1, nullptr, m->dp_ln1g, m->dp_ln1b, D1, (long long)Fd * ld, ld, Fd, lens, batch, max_tx, 1, 0, s);
+    ln(D1, nullptr, m->dp_ln1g, m->dp_ln1b, D1, Fd, 1, 0, um ? &D1_p : nullptr);
     p = mk(D1, Fd, D2, Fd);
     p.pad_left = m->K / 2;
+    if (um) set_in(p, D1_p);
     conv(c, p, m->dp2, batch, max_tx, s);
-    launch_layernorm(D2, nullptr, m->dp_ln2g, m->dp_ln2b, D2, (long long)Fd * ld, ld, Fd, lens, batch, max_tx, 1, 0, s);
+    ln(D2, nullptr, m->dp_ln2g, m->dp_ln2b, D2, Fd, 1, 0, nullptr);
     launch_duration(D2, (long long)Fd * ld, ld, Fd, m->dp_pw, m->dp_pb, lens, batch, max_tx, length_scale, m->n_sqz,
                     c->logw_d, c->wceil_d, c->cum_d, c->ylen_d, s);
-    c->launches += 3;
+    c->launches += 1;
   }
   c->y_len_h.resize(batch);
   B2_CUDA(cudaMemcpyAsync(c->y_len_h.data(), c->ylen_d, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
@@ -793,54 +825,93 @@ static void hifigan_run(const b200tts_hifigan* m, b200tts_call* c, const float* 
       }
       len_mul *= u;
       const int L = Tmax * len_mul;
-      // three resblocks on three streams                          hifi_gan/models.py:191-197
-      B2_CUDA(cudaEventRecord(c->fork, s));
-      for (int j = 0; j < m->n_kernels; ++j) {
-        cudaStream_t sj = j == 0 ? s : c->aux[j - 1];
-        if (j > 0) B2_CUDA(cudaStreamWaitEvent(sj, c->fork, 0));
-        const HifiRB& r = m->rb[i * m->n_kernels + j];
+      // three MRF resblocks                                         hifi_gan/models.py:191-197
+      // tensor-core path: the three branches (k = 3/7/11) share one launch per conv position (blockIdx.z = branch);
+      // fp32 SIMT cross-check path: one launch per conv, branch after branch
+      const int nk = m->n_kernels;
+      auto fill_c1 = [&](int j, int d, ConvParams& p, bool& planes) {
+        const HifiRB& r = m->rb[i * nk + j];
         float* R = bs_[1 + j];
         float* T = bs_[4 + j];
-        for (int d = 0; d < r.ndil; ++d) {
-          const float* xin = d == 0 ? U : R;
-          ConvParams p;
-          p.x = xin; p.x_bs = (long long)cout * Lld; p.x_ld = Lld;
-          p.pre = PRE_LRELU; p.pre_slope = 0.1f;
-          p.lens = frames_d; p.len_mul = len_mul; p.Lin = L;
-          p.dil = r.dil[d]; p.pad_left = (r.k * r.dil[d] - r.dil[d]) / 2;
-          if (m->resblock == 1) {
-            p.y = T; p.y_bs = (long long)cout * Lld; p.y_ld = Lld;
-            const bool pl = ump && r.c1[d].wu && r.c2[d].wu;
-            if (pl) {
-              set_in(p, d == 0 ? U_p : R_p[j]);
-              set_out(p, T_p[j], 0.1f);
-              p.y = nullptr;  // T is only ever read as an MMA operand
-            }
-            conv(c, p, r.c1[d], batch, L, sj);
-            ConvParams q;
-            q.x = T; q.x_bs = (long long)cout * Lld; q.x_ld = Lld;
-            q.pre = PRE_LRELU; q.pre_slope = 0.1f;
-            q.lens = frames_d; q.len_mul = len_mul; q.Lin = L;
-            q.dil = 1; q.pad_left = (r.k - 1) / 2;
-            q.y = R; q.y_bs = (long long)cout * Lld; q.y_ld = Lld;
-            q.res = xin; q.res_bs = (long long)cout * Lld; q.res_ld = Lld;
-            if (pl) {
-              set_in(q, T_p[j]);
-              if (d + 1 < r.ndil) set_out(q, R_p[j], 0.1f);
-            }
-            conv(c, q, r.c2[d], batch, L, sj);
-          } else {  // ResBlock2                                   hifi_gan/models.py:137-142
-            float* dst = (d & 1) ? R : T;  // ping-pong: conv input and output must differ
-            const float* src = d == 0 ? U : ((d & 1) ? T : R);
-            p.x = src;
-            p.y = dst; p.y_bs = (long long)cout * Lld; p.y_ld = Lld;
-            p.res = src; p.res_bs = (long long)cout * Lld; p.res_ld = Lld;
-            conv(c, p, r.c1[d], batch, L, sj);
-          }
+        const float* xin = d == 0 ? U : R;
+        p = ConvParams();
+        p.x = xin; p.x_bs = (long long)cout * Lld; p.x_ld = Lld;
+        p.pre = PRE_LRELU; p.pre_slope = 0.1f;
+        p.lens = frames_d; p.len_mul = len_mul; p.Lin = L;
+        p.dil = r.dil[d]; p.pad_left = (r.k * r.dil[d] - r.dil[d]) / 2;
+        p.y = T; p.y_bs = (long long)cout * Lld; p.y_ld = Lld;
+        planes = ump && r.c1[d].wu && r.c2[d].wu;
+        if (planes) {
+          set_in(p, d == 0 ? U_p : R_p[j]);
+          set_out(p, T_p[j], 0.1f);
+          p.y = nullptr;  // T is only ever read as an MMA operand
         }
-        if (j > 0) {
-          B2_CUDA(cudaEventRecord(c->join[j - 1], sj));
-          B2_CUDA(cudaStreamWaitEvent(s, c->join[j - 1], 0));
+      };
+      auto fill_c2 = [&](int j, int d, ConvParams& q, bool planes) {
+        const HifiRB& r = m->rb[i * nk + j];
+        float* R = bs_[1 + j];
+        float* T = bs_[4 + j];
+        const float* xin = d == 0 ? U : R;
+        q = ConvParams();
+        q.x = T; q.x_bs = (long long)cout * Lld; q.x_ld = Lld;
+        q.pre = PRE_LRELU; q.pre_slope = 0.1f;
+        q.lens = frames_d; q.len_mul = len_mul; q.Lin = L;
+        q.dil = 1; q.pad_left = (r.k - 1) / 2;
+        q.y = R; q.y_bs = (long long)cout * Lld; q.y_ld = Lld;
+        q.res = xin; q.res_bs = (long long)cout * Lld; q.res_ld = Lld;
+        if (planes) {
+          set_in(q, T_p[j]);
+          if (d + 1 < r.ndil) set_out(q, R_p[j], 0.1f);
+        }
+      };
+      auto bind = [&](ConvParams& p, const ConvW& w) {
+        p.w = w.w; p.bias = w.b; p.Cin = w.cin; p.Cout = w.cout; p.K = w.k;
+        p.wu = w.wu; p.um_nt = w.nt; p.um_nsplit = w.nsplit;
+      };
+      const bool batched = m->resblock == 1 && use_umma() && nk == 3 && m->rb[i * nk].c1[0].wu != nullptr &&
+                           !getenv("B200TTS_CONV_TRACE");
+      if (batched) {
+        const int ndil = m->rb[i * nk].ndil;
+        for (int d = 0; d < ndil; ++d) {
+          ConvParams ps[3];
+          bool pl[3];
+          for (int j = 0; j < 3; ++j) {
+            fill_c1(j, d, ps[j], pl[j]);
+            bind(ps[j], m->rb[i * nk + j].c1[d]);
+          }
+          c->launches += launch_conv_umma_batch(ps, 3, batch, L, s);
+          for (int j = 0; j < 3; ++j) {
+            fill_c2(j, d, ps[j], pl[j]);
+            bind(ps[j], m->rb[i * nk + j].c2[d]);
+          }
+          c->launches += launch_conv_umma_batch(ps, 3, batch, L, s);
+        }
+      } else {
+        for (int j = 0; j < nk; ++j) {
+          const HifiRB& r = m->rb[i * nk + j];
+          float* R = bs_[1 + j];
+          float* T = bs_[4 + j];
+          for (int d = 0; d < r.ndil; ++d) {
+            if (m->resblock == 1) {
+              ConvParams p, q;
+              bool pl;
+              fill_c1(j, d, p, pl);
+              conv(c, p, r.c1[d], batch, L, s);
+              fill_c2(j, d, q, pl);
+              conv(c, q, r.c2[d], batch, L, s);
+            } else {  // ResBlock2                                   hifi_gan/models.py:137-142
+              ConvParams p;
+              float* dst = (d & 1) ? R : T;  // ping-pong: conv input and output must differ
+              const float* src = d == 0 ? U : ((d & 1) ? T : R);
+              p.x = src; p.x_bs = (long long)cout * Lld; p.x_ld = Lld;
+              p.pre = PRE_LRELU; p.pre_slope = 0.1f;
+              p.lens = frames_d; p.len_mul = len_mul; p.Lin = L;
+              p.dil = r.dil[d]; p.pad_left = (r.k * r.dil[d] - r.dil[d]) / 2;
+              p.y = dst; p.y_bs = (long long)cout * Lld; p.y_ld = Lld;
+              p.res = src; p.res_bs = (long long)cout * Lld; p.res_ld = Lld;
+              conv(c, p, r.c1[d], batch, L, s);
+            }
+          }
         }
       }
       // the resblock result buffer: ResBlock1 -> R; ResBlock2 with ndil=2 -> last dst = R (d=1)

@@ -74,31 +74,50 @@ void launch_embed(const long long* ids, const int* lens, int batch, int max_tx, 
 // block = 32 time steps x 8 channel groups; each thread keeps its C/8 values in registers.
 // ------------------------------------------------------------------------------------------------
 constexpr int LN_MAXC = 256;
+constexpr int LN_PADL = 40;  // == UM_PADL (conv_umma.cuh)
+
+__device__ __forceinline__ unsigned int ln_cvt_bf16x2(float a, float b) {
+  unsigned int r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+
+// Each thread owns whole 8-channel groups (g = ty + 8*i) of one time step, so that besides the fp32 result it can
+// emit the bf16 split planes [plane][C/8][PADL + rows][8] that the tensor-core convs load by bulk copy.
+// Grid x covers `cover` >= Lmax time steps: blocks past the valid length only write the zero rows of the image.
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ res,
                                                         const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float* __restrict__ y,
                                                         long long bs, int ld, int C, const int* __restrict__ lens,
-                                                        int pre_relu, int post_relu, float eps) {
+                                                        int pre_relu, int post_relu, float eps, unsigned char* planes,
+                                                        long long pl_bs, int pl_kc, int pl_rows, int pl_nsplit,
+                                                        int cover) {
   __shared__ float red[8][33];
   const int b = blockIdx.y;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int t = blockIdx.x * 32 + tx;
-  const bool valid = t < lens[b];
+  const int len = lens[b];
+  const bool valid = t < len;
   const float* xb = x + (size_t)b * bs;
   const float* rb = res ? res + (size_t)b * bs : nullptr;
-  float v[LN_MAXC / 8];
+  const int ngrp = C >> 3;
+  float v[LN_MAXC / 64][8];
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAXC / 8; ++i) {
-    const int c = ty + i * 8;
-    const bool ok = valid && c < C;  // branch-free: all loads of the column are in flight together
-    const size_t off = ok ? (size_t)c * ld + t : 0;
-    float a = xb[off];
-    if (rb) a += rb[off];
-    if (pre_relu) a = fmaxf(a, 0.f);
-    a = ok ? a : 0.f;
-    v[i] = a;
-    s += a;
+  for (int i = 0; i < LN_MAXC / 64; ++i) {
+    const int g = ty + i * 8;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = g * 8 + e;
+      const bool ok = valid && g < ngrp;  // branch-free: all loads of the column are in flight together
+      const size_t off = ok ? (size_t)c * ld + t : 0;
+      float a = xb[off];
+      if (rb) a += rb[off];
+      if (pre_relu) a = fmaxf(a, 0.f);
+      a = ok ? a : 0.f;
+      v[i][e] = a;
+      s += a;
+    }
   }
   red[ty][tx] = s;
   __syncthreads();
@@ -109,11 +128,13 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   __syncthreads();
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAXC / 8; ++i) {
-    const int c = ty + i * 8;
-    if (c < C) {
-      const float d = v[i] - mean;
-      q += d * d;
+  for (int i = 0; i < LN_MAXC / 64; ++i) {
+    if (ty + i * 8 < ngrp) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float d = v[i][e] - mean;
+        q += d * d;
+      }
     }
   }
   red[ty][tx] = q;
@@ -122,25 +143,57 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 #pragma unroll
   for (int j = 0; j < 8; ++j) qt += red[j][tx];
   const float rstd = rsqrtf(qt / (float)C + eps);
-  if (!valid) return;
   float* yb = y + (size_t)b * bs;
+  unsigned char* pb = planes ? planes + (size_t)b * pl_bs : nullptr;
+  const size_t pstride = (size_t)pl_kc * pl_rows * 16;
 #pragma unroll
-  for (int i = 0; i < LN_MAXC / 8; ++i) {
-    const int c = ty + i * 8;
-    if (c < C) {
-      float o = (v[i] - mean) * rstd * gamma[c] + beta[c];
-      if (post_relu) o = fmaxf(o, 0.f);
-      yb[(size_t)c * ld + t] = o;
+  for (int i = 0; i < LN_MAXC / 64; ++i) {
+    const int g = ty + i * 8;
+    if (g >= ngrp) continue;
+    float o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = g * 8 + e;
+      float w = (v[i][e] - mean) * rstd * gamma[c] + beta[c];
+      if (post_relu) w = fmaxf(w, 0.f);
+      o[e] = valid ? w : 0.f;
+      if (valid) yb[(size_t)c * ld + t] = w;
+    }
+    if (pb && t < cover) {
+      unsigned char* base = pb + ((size_t)g * pl_rows + LN_PADL + t) * 16;
+      unsigned int h[4], l[4], l2[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float a0 = o[2 * e], a1 = o[2 * e + 1];
+        h[e] = ln_cvt_bf16x2(a0, a1);
+        const float r0 = a0 - __uint_as_float(h[e] << 16), r1 = a1 - __uint_as_float(h[e] & 0xffff0000u);
+        l[e] = ln_cvt_bf16x2(r0, r1);
+        l2[e] = ln_cvt_bf16x2(r0 - __uint_as_float(l[e] << 16), r1 - __uint_as_float(l[e] & 0xffff0000u));
+      }
+      *reinterpret_cast<uint4*>(base) = make_uint4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<uint4*>(base + pstride) = make_uint4(l[0], l[1], l[2], l[3]);
+      if (pl_nsplit == 3) *reinterpret_cast<uint4*>(base + 2 * pstride) = make_uint4(l2[0], l2[1], l2[2], l2[3]);
+      if (blockIdx.x == 0) {  // zero rows in front of the image: t in [-PADL, 0)
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        for (int r = tx; r < LN_PADL; r += 32)
+          for (int pl = 0; pl < pl_nsplit; ++pl) *reinterpret_cast<uint4*>(pb + pl * pstride + ((size_t)g * pl_rows + r) * 16) = z;
+      }
     }
   }
 }
 
 void launch_layernorm(const float* x, const float* res, const float* gamma, const float* beta, float* y, long long bs,
-                      int ld, int C, const int* lens, int batch, int Lmax, int pre_relu, int post_relu,
-                      cudaStream_t s) {
-  B2_CHECK(C <= LN_MAXC, "layernorm: too many channels");
-  dim3 grid((Lmax + 31) / 32, batch);
-  layernorm_kernel<<<grid, 256, 0, s>>>(x, res, gamma, beta, y, bs, ld, C, lens, pre_relu, post_relu, 1e-4f);
+                      int ld, int C, const int* lens, int batch, int Lmax, int pre_relu, int post_relu, cudaStream_t s,
+                      void* planes, long long pl_bs, int pl_kc, int pl_rows, int pl_nsplit) {
+  B2_CHECK(C <= LN_MAXC && C % 8 == 0, "layernorm: channel count must be a multiple of 8, at most 256");
+  int cover = Lmax;
+  if (planes) {
+    cover = (Lmax + 255) / 256 * 256 + 128;  // rows the consumers may read behind the data must be zero
+    B2_CHECK(LN_PADL + cover <= pl_rows, "layernorm: plane image too short");
+  }
+  dim3 grid((cover + 31) / 32, batch);
+  layernorm_kernel<<<grid, 256, 0, s>>>(x, res, gamma, beta, y, bs, ld, C, lens, pre_relu, post_relu, 1e-4f,
+                                        (unsigned char*)planes, pl_bs, pl_kc, pl_rows, pl_nsplit, cover);
   B2_CUDA(cudaGetLastError());
 }
 

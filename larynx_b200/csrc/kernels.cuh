@@ -8,13 +8,15 @@ namespace b2 {
 int launch_conv1d(const ConvParams& p, int batch, int Lmax, cudaStream_t stream);
 void conv1d_init_attributes();
 int launch_conv_umma(const ConvParams& p, int batch, int Lmax, cudaStream_t stream);
+int launch_conv_umma_batch(const ConvParams* ps, int n, int batch, int Lmax, cudaStream_t stream);
 void conv_umma_init_attributes();
 void attention_init_attributes();
 
 void launch_embed(const long long* ids, const int* lens, int batch, int max_tx, const float* emb, int n_vocab, int H,
                   float* x, long long x_bs, int x_ld, cudaStream_t s);
 void launch_layernorm(const float* x, const float* res, const float* gamma, const float* beta, float* y, long long bs,
-                      int ld, int C, const int* lens, int batch, int Lmax, int pre_relu, int post_relu, cudaStream_t s);
+                      int ld, int C, const int* lens, int batch, int Lmax, int pre_relu, int post_relu, cudaStream_t s,
+                      void* planes = nullptr, long long pl_bs = 0, int pl_kc = 0, int pl_rows = 0, int pl_nsplit = 3);
 void launch_rel_attention(const float* qkv, long long bs, int ld, int H, int n_heads, const float* emb_k,
                           const float* emb_v, int window, const int* lens, int batch, int Tmax, float* out,
                           long long out_bs, int out_ld, cudaStream_t s);

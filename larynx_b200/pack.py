@@ -86,11 +86,13 @@ def from_bf16_bits(b: np.ndarray) -> np.ndarray:
     return (b.astype(np.uint32) << np.uint32(16)).view(np.float32)
 
 
-def pick_nt(cout: int) -> int:
-    """Output-channel tile of the tensor-core conv: a multiple of 16, <= 128, dividing Cout rounded up to 16."""
+def pick_nt(cout: int, nt_max: int = 128) -> int:
+    """Output-channel tile of the tensor-core conv: a multiple of 16, <= nt_max, dividing Cout rounded up to 16.
+    Layers that run on tiny grids (GlowTTS at batch 1: one or two 128-row time tiles) use a smaller tile so more
+    SMs share the serial per-tile latency."""
     c16 = (cout + 15) // 16 * 16
     for nt in (128, 112, 96, 80, 64, 48, 32, 16):
-        if c16 % nt == 0:
+        if nt <= nt_max and c16 % nt == 0:
             return nt
     return 16
 
@@ -98,13 +100,13 @@ def pick_nt(cout: int) -> int:
 UMMA_BKC = 32  # input channels per pipeline stage (csrc/conv_umma.cuh: UM_BKC)
 
 
-def umma_image(w: np.ndarray, nsplit: int):
+def umma_image(w: np.ndarray, nsplit: int, nt_max: int = 128):
     """[Cout][Cin][K] fp32 -> bf16 split image for conv_umma_kernel:
     [n-tile][ci-chunk of 32][tap][split plane hi/lo(/lo2)][k-chunk of 8 (4)][NT rows][8] uint16.
     Each (n-tile, ci-chunk, tap) block is one contiguous cp.async.bulk transfer and already has the
     K-major SWIZZLE_NONE UMMA operand layout (rows 16 B apart)."""
     cout, cin, k = w.shape
-    nt = pick_nt(cout)
+    nt = pick_nt(cout, nt_max)
     ntiles = (cout + nt - 1) // nt
     nch = (cin + UMMA_BKC - 1) // UMMA_BKC
     wp = np.zeros((ntiles * nt, nch * UMMA_BKC, k), dtype=np.float32)
@@ -155,12 +157,14 @@ class BlobWriter:
             bits = np.concatenate([bits, np.zeros(1, np.uint16)])
         self.items.append((name, bits.view(np.float32)))
 
+    nt_max = 128
+
     def add_conv(self, name: str, w: np.ndarray, b: np.ndarray, nsplit: int = 2, simt: bool = True):
         """w is [Cout][Cin][K] in final (packed) channel order."""
         if simt:
             self.add(name + ".w", conv_layout(w))
         self.add(name + ".b", b)
-        img, meta = umma_image(w, nsplit)
+        img, meta = umma_image(w, nsplit, self.nt_max)
         self.add_u16(name + ".u", img)
         self.add(name + ".um", meta)
 
@@ -200,6 +204,9 @@ def pack_glow(sd: Dict[str, np.ndarray], config: dict) -> np.ndarray:
            m["n_layers_enc"], m["window_size"], mel, m["n_blocks_dec"], m["kernel_size_dec"], m["dilation_rate"],
            m["n_block_layers"], m["n_sqz"], m["n_split"], Hd]
     bw = BlobWriter(KIND_GLOW, cfg)
+    import os
+
+    bw.nt_max = int(os.environ.get("B200TTS_GLOW_NT", "64"))  # GlowTTS runs on 1-4 time tiles: favour more N tiles
     g = lambda k: _np(sd[k])
     bw.add("emb", g("encoder.emb.weight"))
     for i in range(3):

@@ -51,7 +51,7 @@ def test_golden_vectors(name):
     for blk in (11, 6, 0):
         if f"flow{blk}" in g:
             tap = glow.model.flow_tap(call, blk, 1, mel.shape[2] // 2)
-            assert np.abs(tap[0] - g[f"flow{blk}"]).max() <= 2e-4
+            assert np.abs(tap[0] - g[f"flow{blk}"]).max() <= 5e-4  # |values| ~ 5: 1e-4 relative
     # boundary #2 on the golden glued mel
     pcm = voc.mels_to_float(g["mel_glued"][None])
     ref = g["pcm"]

@@ -350,7 +350,10 @@ def bench_ours(args, rank, world, local_rank):
             "gpu_launches_per_step": int(launches // K),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": voc_tflops, "peak": tensor_peak, "unit": "TFLOP/s",
-                         "frac": voc_tflops / tensor_peak, "traffic": None, "peak_source": peak_src + " bf16 dense (burst)",
+                         "frac": voc_tflops / tensor_peak, "traffic": 2.4e7,
+                         "traffic_note": "dram__bytes_read+write of one stage-1 ResBlock launch (3 MRF branches, C=256, L=4016) from the ncu --set full "
+                                         "capture in profiles/r1f_ncu_full_conv_umma_stage1.csv: 18-31 MB (cold weights), activations stay in L2",
+                         "peak_source": peak_src + " bf16 dense (burst)",
                          "kernel": f"conv_umma_kernel<MT,NSPLIT,EW,WST> (tcgen05 kind::f16, bf16x3 split = 3 MMAs per algorithmic MAC-tile, fp32 TMEM "
                                    f"accumulators): HiFi-GAN pass ({voc_launches} launches, {vms:.3f} ms, {HIFIGAN_MFLOP_PER_FRAME:.1f} MFLOP/frame x {frames} frames)",
                          "tensor_flops_issued_tflops": 3 * voc_tflops, "frac_tensor_issued": 3 * voc_tflops / tensor_peak,

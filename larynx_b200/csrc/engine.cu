@@ -115,6 +115,7 @@ struct GlowFlow {
 struct GlowEnc {
   ConvW qkv, o, ffn1, ffn2;
   const float *rel_k, *rel_v, *ln1g, *ln1b, *ln2g, *ln2b;
+  const void *relk_img = nullptr, *relv_img = nullptr;  // bf16 3-plane operand images of emb_rel_k / emb_rel_v
 };
 
 struct b200tts_glow {
@@ -358,6 +359,10 @@ static void glow_bind(b200tts_glow* m) {
     e.ffn2 = conv_w(W, s + ".ffn2", m->F, H, m->K);
     e.rel_k = W.get(s + ".rel_k", (size_t)nrel * dk);
     e.rel_v = W.get(s + ".rel_v", (size_t)nrel * dk);
+    if (W.has(s + ".rel_k_img") && dk == 96) {
+      e.relk_img = W.get(s + ".rel_k_img", 3 * 12 * 16 * 8 / 2);
+      e.relv_img = W.get(s + ".rel_v_img", 3 * 12 * 16 * 8 / 2);
+    }
     e.ln1g = W.get(s + ".ln1.g", H); e.ln1b = W.get(s + ".ln1.b", H);
     e.ln2g = W.get(s + ".ln2.g", H); e.ln2b = W.get(s + ".ln2.b", H);
   }
@@ -404,8 +409,10 @@ static void glow_encode_impl(const b200tts_glow* m, b200tts_call* c, const int64
   // bf16 operand images (3-way split: the encoder feeds the bit-exact alignment) written by LN / conv epilogues
   const bool um = use_umma() && H % 32 == 0 && F % 32 == 0 && Fd % 32 == 0;
   const int prow = plane_rows(max_tx, 1);
-  if (um) need += 3 * Arena::pad(B * plane_item_bytes(H, prow, 3), 1) + Arena::pad(B * plane_item_bytes(F, prow, 3), 1) +
-                  Arena::pad(B * plane_item_bytes(Fd, prow, 3), 1);
+  if (um) need += 4 * Arena::pad(B * plane_item_bytes(H, prow, 3), 1) + Arena::pad(B * plane_item_bytes(F, prow, 3), 1) +
+                  Arena::pad(B * plane_item_bytes(Fd, prow, 3), 1) + Arena::pad(B * plane_item_bytes(3 * H, prow, 3), 1);
+  // tcgen05 attention needs the q/k/v image and handles up to 128 phonemes per item; longer batches use the SIMT kernel
+  const bool um_att = um && attn_umma_supported(H, m->n_heads, m->window, max_tx) && !getenv("B200TTS_ATTN_SIMT");
   c->enc.reserve(need + 4096);
   long long* ids_d = c->enc.take<long long>(B * max_tx);
   c->xlen_d = c->enc.take<int>(B);
@@ -423,8 +430,10 @@ static void glow_encode_impl(const b200tts_glow* m, b200tts_call* c, const int64
   float* D1 = c->enc.take<float>(act * Fd);
   float* D2 = c->enc.take<float>(act * Fd);
   c->xm_d = c->enc.take<float>(act * mel);
-  Planes X_p, P_p[2], FF_p, D1_p;
+  Planes X_p, P_p[2], FF_p, D1_p, QKV_p, ATT_p;
   if (um) {
+    QKV_p = take_planes(c->enc, batch, 3 * H, prow, 3);
+    ATT_p = take_planes(c->enc, batch, H, prow, 3);
     X_p = take_planes(c->enc, batch, H, prow, 3);
     P_p[0] = take_planes(c->enc, batch, H, prow, 3);
     P_p[1] = take_planes(c->enc, batch, H, prow, 3);
@@ -479,11 +488,21 @@ static void glow_encode_impl(const b200tts_glow* m, b200tts_call* c, const int64
     const GlowEnc& e = m->enc[i];
     ConvParams p = mk(X, H, QKV, 3 * H);
     if (um) set_in(p, X_p);
+    if (um_att && e.relk_img) {
+      set_out(p, QKV_p, 1.f);
+      p.y = nullptr;  // q, k, v are only ever MMA operands of the attention kernel
+    }
     conv(c, p, e.qkv, batch, max_tx, s);
-    launch_rel_attention(QKV, (long long)3 * H * ld, ld, H, m->n_heads, e.rel_k, e.rel_v, m->window, lens, batch,
-                         max_tx, ATT, (long long)H * ld, ld, s);
+    if (um_att && e.relk_img) {
+      launch_attn_umma(QKV_p.ptr, QKV_p.bs, QKV_p.kc, QKV_p.rows, e.relk_img, e.relv_img, m->window, H, m->n_heads, lens, batch,
+                       ATT_p.ptr, ATT_p.bs, ATT_p.kc, ATT_p.rows, nullptr, 0, 0, s);
+    } else {
+      launch_rel_attention(QKV, (long long)3 * H * ld, ld, H, m->n_heads, e.rel_k, e.rel_v, m->window, lens, batch,
+                           max_tx, ATT, (long long)H * ld, ld, s);
+    }
     c->launches++;
     p = mk(ATT, H, A, H);
+    if (um_att && e.relk_img) set_in(p, ATT_p);
     conv(c, p, e.o, batch, max_tx, s);
     ln(X, A, e.ln1g, e.ln1b, X, H, 0, 0, um ? &X_p : nullptr);
     p = mk(X, H, FF, F);
@@ -1024,6 +1043,7 @@ int b200tts_call_create(int device, b200tts_call** out) {
   conv1d_init_attributes();
   conv_umma_init_attributes();
   attention_init_attributes();
+  attn_umma_init_attributes();
   b200tts_call* c = new b200tts_call();
   c->device = device;
   B2_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));

@@ -124,6 +124,21 @@ def umma_image(w: np.ndarray, nsplit: int, nt_max: int = 128):
     return np.ascontiguousarray(img).reshape(-1), meta
 
 
+def rel_image(e: np.ndarray) -> np.ndarray:
+    """Relative-position embedding [2w+1][96] -> bf16 3-way split operand image [plane][12][16][8] (rows >= 2w+1 zero)."""
+    n, d = e.shape
+    full = np.zeros((16, d), dtype=np.float32)
+    full[:n] = e
+    planes = []
+    rem = full
+    for _ in range(3):
+        bits = to_bf16_bits(rem)
+        planes.append(bits)
+        rem = (rem - from_bf16_bits(bits)).astype(np.float32)
+    img = np.stack(planes, 0).reshape(3, 16, d // 8, 8)  # [plane][row][group][8]
+    return np.ascontiguousarray(np.transpose(img, (0, 2, 1, 3))).reshape(-1)
+
+
 def pixel_shuffle_conv(w: np.ndarray, u: int, k: int) -> np.ndarray:
     """ConvTranspose1d weight [Cin][Cout][k] (stride u, padding (k-u)/2, k == 2u) as ONE ordinary 3-tap conv
     (pad_left 1) with u*Cout packed output channels n = co*u + r:  y[co][t*u + r] = conv3(x)[n][t].
@@ -225,6 +240,10 @@ def pack_glow(sd: Dict[str, np.ndarray], config: dict) -> np.ndarray:
             raise ValueError("heads_share=False relative embeddings are not supported")
         bw.add(f"enc{i}.rel_k", ek[0])
         bw.add(f"enc{i}.rel_v", ev[0])
+        if ek.shape[2] == 96 and ek.shape[1] <= 9:
+            # operand images for the tcgen05 attention: rows r = E[r], [3 planes][12 groups][16 rows][8 channels]
+            bw.add_u16(f"enc{i}.rel_k_img", rel_image(ek[0]))
+            bw.add_u16(f"enc{i}.rel_v_img", rel_image(ev[0]))
         bw.add(f"enc{i}.ln1.g", g(f"encoder.encoder.norm_layers_1.{i}.gamma"))
         bw.add(f"enc{i}.ln1.b", g(f"encoder.encoder.norm_layers_1.{i}.beta"))
         f = f"encoder.encoder.ffn_layers.{i}"

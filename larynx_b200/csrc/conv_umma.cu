@@ -6,22 +6,32 @@
 
 namespace b2 {
 
-template <int MT, int NSPLIT, int EW, int WST>
+template <int MT, int NSPLIT, int EW, int WST, int AST, int G>
 static void set_attr_umma() {
-  B2_CUDA(cudaFuncSetAttribute(conv_umma_kernel<MT, NSPLIT, EW, WST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  B2_CUDA(cudaFuncSetAttribute(conv_umma_kernel<MT, NSPLIT, EW, WST, AST, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 }
+
+// kernel variants (MT, NSPLIT, EW, WST, AST, G)
+#define UMMA_BIG 1, 2, 8, 3, 2, 1        /* large grids: two CTAs per SM */
+#define UMMA_BIG2 2, 2, 8, 6, 2, 1       /* 256-row tiles (kept for experiments) */
+#define UMMA_SMALL128 1, 2, 16, 3, 2, 2  /* small grids, NT = 128: 2 taps (32 KB) per weight slot */
+#define UMMA_SMALL64 1, 2, 16, 3, 3, 5   /* small grids, NT <= 64: up to 5 taps (40 KB) per slot, 3 activation stages */
+#define UMMA_ENC128 1, 3, 16, 3, 2, 1    /* 3-way split (text encoder) */
+#define UMMA_ENC64 1, 3, 16, 3, 2, 3
 
 void conv_umma_init_attributes() {
-  set_attr_umma<1, 2, 8, 3>();
-  set_attr_umma<2, 2, 8, 6>();
-  set_attr_umma<1, 2, 16, 6>();
-  set_attr_umma<1, 3, 16, 4>();
+  set_attr_umma<UMMA_BIG>();
+  set_attr_umma<UMMA_BIG2>();
+  set_attr_umma<UMMA_SMALL128>();
+  set_attr_umma<UMMA_SMALL64>();
+  set_attr_umma<UMMA_ENC128>();
+  set_attr_umma<UMMA_ENC64>();
 }
 
-template <int MT, int NSPLIT, int EW, int WST>
+template <int MT, int NSPLIT, int EW, int WST, int AST, int G>
 static void launch_umma_cfg(const ConvBatch& pb, int batch, int Lmax, cudaStream_t s) {
   const ConvParams& p = pb.p[0];
-  const size_t smem = UmmaCfg<MT>::smem_bytes(NSPLIT, p.um_nt, WST);
+  const size_t smem = UmmaCfg<MT>::smem_bytes(NSPLIT, p.um_nt, WST, AST, G);
   B2_CHECK(smem <= 227 * 1024, "conv_umma: shared memory budget exceeded");
   const int ntiles = (p.Cout + p.um_nt - 1) / p.um_nt;
   dim3 grid((Lmax + MT * 128 - 1) / (MT * 128), ntiles, batch * pb.n);
@@ -35,7 +45,7 @@ static void launch_umma_cfg(const ConvBatch& pb, int batch, int Lmax, cudaStream
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  B2_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<MT, NSPLIT, EW, WST>, pb));
+  B2_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<MT, NSPLIT, EW, WST, AST, G>, pb));
 }
 
 int launch_conv_umma_batch(const ConvParams* ps, int n, int batch, int Lmax, cudaStream_t stream) {
@@ -67,13 +77,16 @@ int launch_conv_umma_batch(const ConvParams* ps, int n, int batch, int Lmax, cud
     ew16_max = e2 ? atoll(e2) : 148;
   }
   if (p.um_nsplit == 3) {
-    launch_umma_cfg<1, 3, 16, 4>(pb, batch, Lmax, stream);
+    if (p.um_nt <= 64) launch_umma_cfg<UMMA_ENC64>(pb, batch, Lmax, stream);
+    else launch_umma_cfg<UMMA_ENC128>(pb, batch, Lmax, stream);
   } else if (ctas2 >= mt2_min) {
-    launch_umma_cfg<2, 2, 8, 6>(pb, batch, Lmax, stream);
+    launch_umma_cfg<UMMA_BIG2>(pb, batch, Lmax, stream);
   } else if (ctas1 > ew16_max) {
-    launch_umma_cfg<1, 2, 8, 3>(pb, batch, Lmax, stream);
+    launch_umma_cfg<UMMA_BIG>(pb, batch, Lmax, stream);
+  } else if (p.um_nt <= 64) {
+    launch_umma_cfg<UMMA_SMALL64>(pb, batch, Lmax, stream);
   } else {
-    launch_umma_cfg<1, 2, 16, 6>(pb, batch, Lmax, stream);
+    launch_umma_cfg<UMMA_SMALL128>(pb, batch, Lmax, stream);
   }
   B2_CUDA(cudaGetLastError());
   return 1;

@@ -32,8 +32,7 @@ namespace b2 {
 constexpr int UM_BKC = 32;               // input channels per A stage
 constexpr int UM_KCH = UM_BKC / 8;       // 16-byte k-chunks per stage
 constexpr int UM_HALO = 80;              // max (K-1)*dil
-constexpr int UM_ASTAGES = 2;
-constexpr int UM_WSTAGES_MAX = 8;
+constexpr int UM_WSTAGES_MAX = 16;
 constexpr int UM_PADL = 40;              // zero rows in front of a plane image (>= any pad_left)
 constexpr int UM_TAIL = 128;             // zero rows written behind the last tile (>= UM_HALO)
 
@@ -45,8 +44,9 @@ struct UmmaCfg {
   static constexpr int RA = MT * 128 + UM_HALO;  // rows of the A image
   static size_t a_stage_bytes(int nsplit) { return (size_t)nsplit * UM_KCH * RA * 16; }
   static size_t w_stage_bytes(int nsplit, int NT) { return (size_t)nsplit * UM_KCH * NT * 16; }
-  static size_t smem_bytes(int nsplit, int NT, int wstages) {
-    return UM_ASTAGES * a_stage_bytes(nsplit) + wstages * w_stage_bytes(nsplit, NT) + 256 + 4 * (256 + 16 + 2 * 256);
+  static size_t smem_bytes(int nsplit, int NT, int wstages, int astages, int taps_per_stage) {
+    return astages * a_stage_bytes(nsplit) + (size_t)wstages * taps_per_stage * w_stage_bytes(nsplit, NT) + 384 +
+           4 * (256 + 16 + 2 * 256);
   }
 };
 
@@ -161,7 +161,9 @@ __device__ __forceinline__ void plane_store4(const PlaneOut& po, int kc, int bof
 // MT: 128-row tiles per CTA; NSPLIT: bf16 planes per operand; EW: epilogue/gather warps (8 or 16);
 // WST: weight ring depth.  <1,2,8,3> fits two CTAs per SM (large grids); EW = 16 variants are for small grids
 // where a CTA has the SM to itself and the serial latency of one tile is what matters.
-template <int MT, int NSPLIT, int EW, int WST>
+// AST: activation ring depth (per 32-channel chunk); G: conv taps per weight stage (one bulk copy, one wait, one
+// commit per stage — the single MMA-issuing warp is the serial resource of the main loop, so fewer, fatter stages).
+template <int MT, int NSPLIT, int EW, int WST, int AST, int G>
 __global__ void __launch_bounds__(EW * 32 + 64, (MT == 1 && EW == 8) ? 2 : 1) conv_umma_kernel(const __grid_constant__ ConvBatch pb) {
   using namespace umma;
   const ConvParams& p = pb.p[blockIdx.z / pb.zb];
@@ -182,15 +184,17 @@ __global__ void __launch_bounds__(EW * 32 + 64, (MT == 1 && EW == 8) ? 2 : 1) co
   const uint32_t w_split_bytes = UM_KCH * NT * 16;
   const uint32_t w_stage = NSPLIT * w_split_bytes;
   unsigned char* sA = smem_raw;
-  unsigned char* sW = smem_raw + UM_ASTAGES * a_stage;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + UM_WSTAGES * w_stage);
-  uint64_t* a_full = bars;        // [2]
-  uint64_t* a_empty = bars + 2;   // [2]
-  uint64_t* w_full = bars + 4;    // [UM_WSTAGES]
-  uint64_t* w_empty = bars + 12;  // [UM_WSTAGES]
-  uint64_t* acc_full = bars + 20; // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
-  float* s_bias = reinterpret_cast<float*>(bars + 32);  // [NT] bias of this N tile
+  const uint32_t w_ring = G * w_stage;  // bytes of one weight ring slot (G taps)
+  unsigned char* sW = smem_raw + AST * a_stage;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + UM_WSTAGES * w_ring);
+  uint64_t* a_full = bars;        // [AST <= 4]
+  uint64_t* a_empty = bars + 4;   // [AST <= 4]
+  uint64_t* w_full = bars + 8;    // [UM_WSTAGES]
+  uint64_t* w_empty = bars + 24;  // [UM_WSTAGES]
+  uint64_t* acc_full = bars + 40; // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 41);
+  float* s_bias = reinterpret_cast<float*>(bars + 44);  // [NT] bias of this N tile
+  static_assert(AST <= 4, "activation ring too deep");
   float* s_inv = s_bias + 256;                          // [16]      coupling: W^-1
   float* s_anb = s_inv + 16;                            // [2*half]  ActNorm bias
   float* s_ans = s_anb + 256;                           // [2*half]  ActNorm exp(-logs)
@@ -210,7 +214,7 @@ __global__ void __launch_bounds__(EW * 32 + 64, (MT == 1 && EW == 8) ? 2 : 1) co
 
   if (tid == 0) UM_TRACE(0);
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < AST; ++i) {
       mbar_init(&a_full[i], planes_in ? 1 : UM_NPROD / 32);
       mbar_init(&a_empty[i], 1);
     }
@@ -244,13 +248,15 @@ __global__ void __launch_bounds__(EW * 32 + 64, (MT == 1 && EW == 8) ? 2 : 1) co
     // ===================== weight producer =====================
     if (lane == 0) {
       const unsigned char* gw = reinterpret_cast<const unsigned char*>(p.wu) + (size_t)ntile * nch * K * w_stage;
-      int n = 0;
+      int s = 0;
+      uint32_t ph = 1;  // parity to wait for on w_empty (fresh barrier: passes)
       for (int c = 0; c < nch; ++c)
-        for (int k = 0; k < K; ++k, ++n) {
-          const int s = n % UM_WSTAGES;
-          mbar_wait(&w_empty[s], ((n / UM_WSTAGES) & 1) ^ 1);
-          mbar_arrive_expect_tx(&w_full[s], w_stage);
-          bulk_g2s(sW + (size_t)s * w_stage, gw + (size_t)n * w_stage, w_stage, &w_full[s]);
+        for (int k0 = 0; k0 < K; k0 += G) {
+          const uint32_t bytes = (uint32_t)min(G, K - k0) * w_stage;  // taps of one chunk are contiguous in the image
+          mbar_wait(&w_empty[s], ph);
+          mbar_arrive_expect_tx(&w_full[s], bytes);
+          bulk_g2s(sW + (size_t)s * w_ring, gw + ((size_t)c * K + k0) * w_stage, bytes, &w_full[s]);
+          if (++s == UM_WSTAGES) { s = 0; ph ^= 1; }
         }
     }
   } else if (warp == W_MMA) {
@@ -265,45 +271,50 @@ __global__ void __launch_bounds__(EW * 32 + 64, (MT == 1 && EW == 8) ? 2 : 1) co
       const uint32_t a_ks = (2 * RA * 16) >> 4, b_ks = (2 * NT * 16) >> 4;  // next K=16 step
       const uint32_t a_sp = a_split_bytes >> 4, b_sp = w_split_bytes >> 4;  // next split plane
       const uint32_t a_mt = (128 * 16) >> 4;                                // next 128-row tile
-      int n = 0;
+      int ws = 0, as = 0;
+      uint32_t wph = 0, aph = 0;
       for (int c = 0; c < nch; ++c) {
-        const int as = c & 1;
-        mbar_wait(&a_full[as], (c >> 1) & 1);
+        mbar_wait(&a_full[as], aph);
         tc_fence_after();
         if (c == 0 && lane == 0) UM_TRACE(3);
         const uint64_t a_c = a_desc0 + ((as * a_stage) >> 4);
-        for (int k = 0; k < K; ++k, ++n) {
-          const int s = n % UM_WSTAGES;
-          mbar_wait(&w_full[s], (n / UM_WSTAGES) & 1);
+        for (int k0 = 0; k0 < K; k0 += G) {
+          mbar_wait(&w_full[ws], wph);
           tc_fence_after();
-          const uint64_t a_k = a_c + (uint32_t)(k * dil);  // conv tap: shift the image by k*dil rows of 16 B
-          const uint64_t b_k = b_desc0 + ((s * w_stage) >> 4);
-          const uint32_t first = (c == 0 && k == 0) ? 0u : 1u;
+          const int cnt = min(G, K - k0);
           if (elect_one()) {
+            for (int kk = 0; kk < cnt; ++kk) {
+              const int k = k0 + kk;
+              const uint64_t a_k = a_c + (uint32_t)(k * dil);  // conv tap: shift the image by k*dil rows of 16 B
+              const uint64_t b_k = b_desc0 + ((ws * w_ring + kk * w_stage) >> 4);
+              const uint32_t first = (c == 0 && k == 0) ? 0u : 1u;
 #pragma unroll
-            for (int ks = 0; ks < UM_BKC / 16; ++ks) {
+              for (int ks = 0; ks < UM_BKC / 16; ++ks) {
 #pragma unroll
-              for (int mt = 0; mt < MT; ++mt) {
-                const uint64_t a0 = a_k + ks * a_ks + mt * a_mt, b0 = b_k + ks * b_ks;
-                const uint32_t acc0 = ks == 0 ? first : 1u;
-                const uint32_t d0 = tmem + (0 * MT + mt) * NT, d1 = tmem + (1 * MT + mt) * NT;
-                mma_bf16_ss(d0, a0, b0, idesc, acc0);                // hi*hi
-                mma_bf16_ss(d1, a0, b0 + b_sp, idesc, acc0);         // hi*lo
-                mma_bf16_ss(d1, a0 + a_sp, b0, idesc, 1u);           // lo*hi
-                if (NSPLIT == 3) {
-                  const uint32_t d2 = tmem + (2 * MT + mt) * NT;
-                  mma_bf16_ss(d2, a0 + a_sp, b0 + b_sp, idesc, acc0);  // lo*lo
-                  mma_bf16_ss(d2, a0, b0 + 2 * b_sp, idesc, 1u);       // hi*lo2
-                  mma_bf16_ss(d2, a0 + 2 * a_sp, b0, idesc, 1u);       // lo2*hi
+                for (int mt = 0; mt < MT; ++mt) {
+                  const uint64_t a0 = a_k + ks * a_ks + mt * a_mt, b0 = b_k + ks * b_ks;
+                  const uint32_t acc0 = ks == 0 ? first : 1u;
+                  const uint32_t d0 = tmem + (0 * MT + mt) * NT, d1 = tmem + (1 * MT + mt) * NT;
+                  mma_bf16_ss(d0, a0, b0, idesc, acc0);                // hi*hi
+                  mma_bf16_ss(d1, a0, b0 + b_sp, idesc, acc0);         // hi*lo
+                  mma_bf16_ss(d1, a0 + a_sp, b0, idesc, 1u);           // lo*hi
+                  if (NSPLIT == 3) {
+                    const uint32_t d2 = tmem + (2 * MT + mt) * NT;
+                    mma_bf16_ss(d2, a0 + a_sp, b0 + b_sp, idesc, acc0);  // lo*lo
+                    mma_bf16_ss(d2, a0, b0 + 2 * b_sp, idesc, 1u);       // hi*lo2
+                    mma_bf16_ss(d2, a0 + 2 * a_sp, b0, idesc, 1u);       // lo2*hi
+                  }
                 }
               }
             }
-            mma_commit(&w_empty[s]);  // frees the weight stage when these MMAs have completed
+            mma_commit(&w_empty[ws]);  // frees the weight slot when these MMAs have completed
           }
           __syncwarp();
+          if (++ws == UM_WSTAGES) { ws = 0; wph ^= 1; }
         }
         if (elect_one()) mma_commit(&a_empty[as]);  // frees the activation stage
         __syncwarp();
+        if (++as == AST) { as = 0; aph ^= 1; }
       }
       if (elect_one()) mma_commit(acc_full);
       if (lane == 0) UM_TRACE(4);
@@ -316,9 +327,10 @@ __global__ void __launch_bounds__(EW * 32 + 64, (MT == 1 && EW == 8) ? 2 : 1) co
       if (tid == 0) {
         const unsigned char* xp = reinterpret_cast<const unsigned char*>(p.xp) + (size_t)b * p.xp_bs;
         const long long row0 = (long long)t0 - p.pad_left + UM_PADL;
-        for (int c = 0; c < nch; ++c) {
-          const int as = c & 1;
-          mbar_wait(&a_empty[as], ((c >> 1) & 1) ^ 1);
+        int as = 0;
+        uint32_t aph = 1;
+        for (int c = 0; c < nch; ++c, as = (as + 1 == AST ? 0 : as + 1), aph ^= (as == 0)) {
+          mbar_wait(&a_empty[as], aph);
           mbar_arrive_expect_tx(&a_full[as], a_stage);
           unsigned char* dst = sA + (size_t)as * a_stage;
           for (int sp = 0; sp < NSPLIT; ++sp)
@@ -337,9 +349,10 @@ __global__ void __launch_bounds__(EW * 32 + 64, (MT == 1 && EW == 8) ? 2 : 1) co
       const float* xb3 = p.x3 ? p.x3 + (size_t)b * p.x_bs : nullptr;
       const int rows_used = MT * 128 + (K - 1) * dil;
       const bool three = xb2 != nullptr && xb3 != nullptr;  // MRF mean of three inputs (uniform)
-      for (int c = 0; c < nch; ++c) {
-        const int as = c & 1;
-        mbar_wait(&a_empty[as], ((c >> 1) & 1) ^ 1);
+      int as = 0;
+      uint32_t aph = 1;
+      for (int c = 0; c < nch; ++c, as = (as + 1 == AST ? 0 : as + 1), aph ^= (as == 0)) {
+        mbar_wait(&a_empty[as], aph);
         unsigned char* dst = sA + (size_t)as * a_stage;
         constexpr int NTASK = (UM_KCH * RA + UM_NPROD - 1) / UM_NPROD;
         constexpr int TB = NTASK < 4 ? NTASK : (MT == 1 ? 4 : 3);  // tasks per batch: TB x 8 loads in flight per thread

@@ -133,6 +133,30 @@ def test_ragged_batch_equals_per_utterance():
         assert np.array_equal(single["audio"][0], out["audio"][i])
 
 
+def test_batch32_variable_lengths():
+    """BASELINE config 3 shape: 32 utterances of 64..256 phonemes in one padded/ragged batch."""
+    glow, voc = common.product_glow(), common.product_hifi()
+    rs = np.random.RandomState(1234)
+    lens = rs.randint(64, 257, size=32)
+    rows = [synth.bench_ids(int(n), seed=300 + i) for i, n in enumerate(lens)]
+    glue = host.MelGlue.from_config(common.glow_cfg()["audio"])
+    eps1 = synth.seeded_eps(2048, seed=5)
+    eps = np.ascontiguousarray(np.broadcast_to(eps1, (32,) + eps1.shape))
+    out = host.synthesize_batch(glow, voc, glue, rows, 0.667, 1.0, eps=eps, want_mel=True, want_float=True)
+    checked = 0
+    for i in (0, 13, 31):
+        o = _oracle(rows[i], 0.667, 1.0, eps1)
+        w = np.exp(o["logw"].reshape(-1))
+        if np.abs(w - np.round(w)).min() <= 1e-4:
+            continue  # a legitimate ceil() flip is possible on this draw
+        assert out["mel"][i].shape == o["mel"][0].shape
+        assert np.abs(out["mel"][i] - o["mel"][0]).max() <= TOL_MEL
+        assert np.abs(out["pcm"][i] - o["pcm"]).max() <= 20 * TOL_PCM
+        checked += 1
+    assert checked >= 2
+    assert all(a.shape[0] == int(y) * 256 for a, y in zip(out["audio"], out["y_len"]))
+
+
 def test_vocoder_ragged_batch_has_no_cross_talk():
     voc = common.product_hifi()
     rs = np.random.RandomState(5)

@@ -887,9 +887,32 @@ static void hifigan_run(const b200tts_hifigan* m, b200tts_call* c, const float* 
         p.w = w.w; p.bias = w.b; p.Cin = w.cin; p.Cout = w.cout; p.K = w.k;
         p.wu = w.wu; p.um_nt = w.nt; p.um_nsplit = w.nsplit;
       };
-      const bool batched = m->resblock == 1 && use_umma() && nk == 3 && m->rb[i * nk].c1[0].wu != nullptr &&
+      const bool umma_rb = m->resblock == 1 && use_umma() && nk == 3 && m->rb[i * nk].c1[0].wu != nullptr &&
                            !getenv("B200TTS_CONV_TRACE");
-      if (batched) {
+      // Large stages: run the branches one after the other (branch-major) so the live working set (U + one
+      // branch's R/T images) stays inside the 126 MB L2; small stages: one launch covers the three branches so the
+      // grid fills the GPU.
+      static long long seq_min = -1;
+      if (seq_min < 0) {
+        const char* e = getenv("B200TTS_RB_SEQ_MIN");
+        seq_min = e ? atoll(e) : (1LL << 40);
+      }
+      const long long tiles_per_branch = (long long)((L + 127) / 128) * batch * ((cout + 127) / 128);
+      const bool batched = umma_rb && tiles_per_branch < seq_min;
+      if (umma_rb && !batched) {
+        const int ndil = m->rb[i * nk].ndil;
+        for (int j = 0; j < 3; ++j)
+          for (int d = 0; d < ndil; ++d) {
+            ConvParams p1, p2;
+            bool pl;
+            fill_c1(j, d, p1, pl);
+            bind(p1, m->rb[i * nk + j].c1[d]);
+            c->launches += launch_conv_umma_batch(&p1, 1, batch, L, s);
+            fill_c2(j, d, p2, pl);
+            bind(p2, m->rb[i * nk + j].c2[d]);
+            c->launches += launch_conv_umma_batch(&p2, 1, batch, L, s);
+          }
+      } else if (batched) {
         const int ndil = m->rb[i * nk].ndil;
         for (int d = 0; d < ndil; ++d) {
           ConvParams ps[3];

@@ -5,8 +5,9 @@ Same constructor `(config: VocoderModelConfig, executor=None)` and the same
 (larynx/hifi_gan.py:130-169), including the peak normalisation of
 `audio_float_to_int16` (larynx/audio.py:118-125), which runs on the device.
 
-The spectral-subtraction denoiser (larynx/hifi_gan.py:158-203) is SURVEY.md §8(f) "next": a
-non-zero `denoiser_strength` raises instead of silently returning un-denoised audio.
+The spectral-subtraction denoiser (larynx/hifi_gan.py:158-203, the CLI/server default strength is 0.005) runs on
+the host in numpy exactly like the reference's (larynx_b200/denoise.py); its bias spectrum comes from one extra
+vocoder call on an all-zero mel at first use.  A device-side STFT is SURVEY.md §8(f) "next".
 """
 from __future__ import annotations
 
@@ -17,6 +18,7 @@ from pathlib import Path
 
 import numpy as np
 
+from . import denoise as _denoise
 from . import pack
 from .constants import ARRAY_OR_TENSOR, SettingsType, VocoderModel, VocoderModelConfig
 from .engine import CALLS, HifiGanModel
@@ -44,6 +46,15 @@ class HiFiGanVocoder(VocoderModel):
         self.model = HifiGanModel(blob, self.device)
         self.mel_channels = self.model.mel_channels
         self.denoiser_strength = float(getattr(config, "denoiser_strength", 0.0) or 0.0) if config is not None else 0.0
+        self.bias_spec: typing.Optional[np.ndarray] = None
+        self._bias_lock = __import__("threading").Lock()
+
+    def maybe_init_denoiser(self):
+        """larynx/hifi_gan.py:181-203: bias spectrum = first STFT frame of vocoder(zeros[1, mel, 88])."""
+        with self._bias_lock:
+            if self.bias_spec is None:
+                zeros = np.zeros((1, self.mel_channels, 88), dtype=np.float32)
+                self.bias_spec = _denoise.bias_spectrum(self.mels_to_float(zeros)[None, :])
 
     def mels_to_audio(self, mels: ARRAY_OR_TENSOR, settings: typing.Optional[SettingsType] = None) -> np.ndarray:
         """Convert mel spectrograms to int16 audio."""
@@ -53,13 +64,17 @@ class HiFiGanVocoder(VocoderModel):
         denoiser_strength = self.denoiser_strength
         if settings:
             denoiser_strength = float(settings.get("denoiser_strength", denoiser_strength))
-        if denoiser_strength > 0:
-            raise NotImplementedError("denoiser_strength > 0 is not implemented in larynx_b200 (use denoiser_strength=0)")
         m = np.ascontiguousarray(mels, dtype=np.float32)
         if m.ndim == 2:
             m = m[None]
         assert m.ndim == 3 and m.shape[0] == 1 and m.shape[1] == self.mel_channels, m.shape
         t = m.shape[2]
+        if denoiser_strength > 0 and t > 0:
+            # float waveform from the device, then the reference's host-side STFT denoiser and int16 conversion
+            self.maybe_init_denoiser()
+            audio = self.mels_to_float(m)[None, :]
+            audio = _denoise.denoise(audio, self.bias_spec, denoiser_strength)
+            return _denoise.audio_float_to_int16(audio).squeeze()
         audio = np.zeros(t * self.model.hop, dtype=np.int16)
         if t == 0:
             return audio

@@ -319,6 +319,45 @@ def hifigan_forward(sd: SD, cfg: dict, mel: Tensor, taps: Optional[dict] = None)
 
 
 # -----------------------------------------------------------------------------
+# denoiser (host numpy in the reference too)
+# -----------------------------------------------------------------------------
+
+
+def stft_frames(x: np.ndarray, fft_size: int = 1024, hop: int = 256) -> np.ndarray:
+    """larynx/audio.py:232-248 — Hann window, frames range(0, len(x) - fft_size, hop); rows = time slices."""
+    window = np.hanning(fft_size)
+    return np.array([np.fft.rfft(window * x[i : i + fft_size]) for i in range(0, len(x) - fft_size, hop)])
+
+
+def denoise_reference(audio: np.ndarray, bias_spec: np.ndarray, strength: float) -> np.ndarray:
+    """larynx/hifi_gan.py:171-179 with transform (audio.py:291-306) and inverse/istft (audio.py:251-288).
+    audio [1, N] -> [1, n_t*256 + 1024] float64."""
+    spec = stft_frames(audio[0]).T
+    mag = np.sqrt(spec.real ** 2 + spec.imag ** 2)[None]
+    phase = np.arctan2(spec.imag, spec.real)[None]
+    mag = np.clip(mag - bias_spec * strength, a_min=0.0, a_max=None)
+    n_f = mag.shape[1]
+    comb = np.concatenate([mag * np.cos(phase), mag * np.sin(phase)], axis=1)
+    x = np.empty([1, n_f, comb.shape[2]], dtype=np.complex64)
+    x.real = comb[:, :n_f]
+    x.imag = comb[:, n_f:]
+    X = x[0].T
+    window = np.hanning(1024)
+    out = np.zeros(int(X.shape[0] * 256 + 1024))
+    for n, i in enumerate(range(0, len(out) - 1024, 256)):
+        out[i : i + 1024] += window * np.real(np.fft.irfft(X[n]))
+    return out[None, :]
+
+
+def denoiser_bias_spec(hifi_sd: SD, hifi_cfg: dict) -> np.ndarray:
+    """larynx/hifi_gan.py:181-203 — first STFT frame of the vocoder run on zeros [1, 80, 88]."""
+    bias_audio = hifigan_forward(hifi_sd, hifi_cfg, torch.zeros(1, 80, 88)).squeeze(0).numpy()
+    spec = stft_frames(bias_audio[0]).T
+    mag = np.sqrt(spec.real ** 2 + spec.imag ** 2)[None]
+    return mag[:, :, 0][:, :, None]
+
+
+# -----------------------------------------------------------------------------
 # whole path (== larynx/__init__.py:214-285 _sentence_task without logging / SSML pauses)
 # -----------------------------------------------------------------------------
 

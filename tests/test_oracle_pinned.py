@@ -117,3 +117,26 @@ def test_reference_batched_equals_single():
     assert int(both["y_lengths"][0]) == ty
     assert np.abs(both["mel"][0, :, :ty].numpy() - one["mel"][0].numpy()).max() < 2e-5
     assert float(both["mel"][0, :, ty:].abs().max()) == 0.0
+
+
+def test_denoiser_product_equals_oracle_and_reference():
+    """larynx_b200/denoise.py (vectorised host mirror) vs the loop-form restatement, and vs the reference's own
+    transform/inverse (larynx/audio.py:270-306) where it can be imported."""
+    from larynx_b200 import denoise
+
+    rs = np.random.RandomState(3)
+    audio = (rs.randn(1, 256 * 41) * 0.3).astype(np.float32)
+    bias = np.abs(rs.randn(1, 513, 1)) * 0.5
+    a = denoise.denoise(audio, bias, 0.7)
+    b = port.denoise_reference(audio, bias, 0.7)
+    assert a.shape == b.shape == (1, 256 * 41)
+    assert np.abs(a - b).max() < 1e-12
+    assert np.array_equal(denoise.audio_float_to_int16(a), port.float_to_int16(b))
+    assert denoise.denoise(np.zeros((1, 300), np.float32), bias, 0.5).shape == (1, 1024)  # shorter than one frame
+    if ref_harness.available():
+        ref_harness.import_reference()
+        import larynx.audio as la
+
+        m, p = la.transform(audio)
+        r = la.inverse(np.clip(m - bias * 0.7, 0, None), p)
+        assert np.abs(r - a).max() < 1e-12

@@ -99,8 +99,6 @@ def test_edge_cases():
     mel = glow.phonemes_to_mels(ids, {"noise_scale": 0.0, "length_scale": 0.05})
     assert mel.shape == o["mel"].shape == (1, 80, 4)
     assert np.abs(mel - o["mel"]).max() <= TOL_MEL
-    with pytest.raises(NotImplementedError):
-        voc.mels_to_audio(m1, {"denoiser_strength": 0.01})
     with pytest.raises(Exception):
         voc.model.infer(engine.CALLS.get(0), m1, np.array([5], dtype=np.int32), 1, 1, None, np.zeros(256, np.int16), 256)
 
@@ -155,6 +153,19 @@ def test_batch32_variable_lengths():
         checked += 1
     assert checked >= 2
     assert all(a.shape[0] == int(y) * 256 for a, y in zip(out["audio"], out["y_len"]))
+
+
+def test_denoiser_matches_reference_flow():
+    """CLI/server default: denoiser_strength = 0.005 (larynx/__main__.py:512-516) -> larynx/hifi_gan.py:158-179."""
+    g = np.load(os.path.join(GOLDEN, "ljspeech_fixture28.npz"))
+    voc = common.product_hifi()
+    audio = voc.mels_to_audio(g["mel_glued"][None], {"denoiser_strength": 0.005})
+    bias = port.denoiser_bias_spec(common.oracle_hifi_sd(), common.hifi_cfg())
+    pcm = port.hifigan_forward(common.oracle_hifi_sd(), common.hifi_cfg(), torch.from_numpy(g["mel_glued"][None])).squeeze(0).numpy()
+    ref = port.float_to_int16(port.denoise_reference(pcm, bias, 0.005)).squeeze()
+    assert audio.dtype == np.int16 and audio.shape == ref.shape
+    assert np.abs(voc.bias_spec - bias).max() <= 1e-3 * max(1.0, float(bias.max()))
+    assert np.abs(audio.astype(np.int32) - ref.astype(np.int32)).max() <= _i16_tol(pcm, 2 * TOL_PCM)
 
 
 def test_vocoder_ragged_batch_has_no_cross_talk():

@@ -59,7 +59,14 @@ int launch_conv_umma_batch(const ConvParams* ps, int n, int batch, int Lmax, cud
     B2_CHECK((p.K - 1) * p.dil <= UM_HALO, "conv_umma: receptive field too wide");
     B2_CHECK(p.pad_left <= UM_PADL, "conv_umma: left padding too wide");
     B2_CHECK(p.n_phase == 1, "conv_umma: transposed convs are packed as pixel-shuffle convs");
-    if (p.xp) B2_CHECK(p.xp_kc >= (p.Cin + 31) / 32 * 4, "conv_umma: input plane image too narrow");
+    if (p.xp) {
+      B2_CHECK(p.xp_kc >= (p.Cin + 31) / 32 * 4, "conv_umma: input plane image too narrow");
+      B2_CHECK(p.xp_rows >= UM_PADL + (Lmax + 127) / 128 * 128 + UM_HALO, "conv_umma: input plane image too short");
+    }
+    if (p.yp) {
+      const int u = p.pix > 1 ? p.pix : 1;
+      B2_CHECK(p.yp_rows >= UM_PADL + ((Lmax + 127) / 128 * 128) * u + UM_TAIL, "conv_umma: output plane image too short");
+    }
     B2_CHECK(p.Cout == ps[0].Cout && p.um_nt == ps[0].um_nt && p.um_nsplit == ps[0].um_nsplit && p.Cin == ps[0].Cin,
              "conv_umma: convs of one launch must share their geometry");
     pb.p[i] = p;
@@ -69,13 +76,9 @@ int launch_conv_umma_batch(const ConvParams* ps, int n, int batch, int Lmax, cud
   const int ntiles = (p.Cout + p.um_nt - 1) / p.um_nt;
   const long long ctas1 = (long long)((Lmax + 127) / 128) * ntiles * batch * n;
   const long long ctas2 = (long long)((Lmax + 255) / 256) * ntiles * batch * n;
-  static long long mt2_min = -1, ew16_max = -1;
-  if (mt2_min < 0) {
-    const char* e1 = getenv("B200TTS_MT2_MIN");
-    const char* e2 = getenv("B200TTS_EW16_MAX");
-    mt2_min = e1 ? atoll(e1) : (1LL << 40);  // measured: two co-resident 128-row CTAs per SM beat one 256-row CTA
-    ew16_max = e2 ? atoll(e2) : 148;
-  }
+  // tuning knobs (thread-safe one-time init); measured: two co-resident 128-row CTAs per SM beat one 256-row CTA
+  static const long long mt2_min = [] { const char* e = getenv("B200TTS_MT2_MIN"); return e ? atoll(e) : (1LL << 40); }();
+  static const long long ew16_max = [] { const char* e = getenv("B200TTS_EW16_MAX"); return e ? atoll(e) : 148LL; }();
   if (p.um_nsplit == 3) {
     if (p.um_nt <= 64) launch_umma_cfg<UMMA_ENC64>(pb, batch, Lmax, stream);
     else launch_umma_cfg<UMMA_ENC128>(pb, batch, Lmax, stream);

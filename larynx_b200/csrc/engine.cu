@@ -280,13 +280,18 @@ static void set_out(ConvParams& p, const Planes& pl, float slope, const Planes* 
   if (second) p.yp2 = second->ptr;
 }
 
-static int g_conv_mode = -1;  // 0 = fp32 SIMT everywhere, 1 = tcgen05 where a weight image exists
+// B200TTS_CONV=simt selects the fp32 SIMT cross-check path everywhere; default: tcgen05 where a weight image exists.
+// (function-local statics: initialised once, thread-safe since C++11 — calls arrive from many host threads)
 static bool use_umma() {
-  if (g_conv_mode < 0) {
+  static const bool on = [] {
     const char* e = getenv("B200TTS_CONV");
-    g_conv_mode = (e && strcmp(e, "simt") == 0) ? 0 : 1;
-  }
-  return g_conv_mode == 1;
+    return !(e && strcmp(e, "simt") == 0);
+  }();
+  return on;
+}
+static bool conv_trace() {
+  static const bool on = getenv("B200TTS_CONV_TRACE") != nullptr;
+  return on;
 }
 
 static void conv(b200tts_call* c, ConvParams& p, const ConvW& w, int batch, int Lmax, cudaStream_t s) {
@@ -299,9 +304,7 @@ static void conv(b200tts_call* c, ConvParams& p, const ConvW& w, int batch, int 
     p.wu = w.wu;
     p.um_nt = w.nt;
     p.um_nsplit = w.nsplit;
-    static int trace = -1;
-    if (trace < 0) trace = getenv("B200TTS_CONV_TRACE") ? 1 : 0;
-    if (trace) {  // debug: per-phase timestamps of CTA (0,0,0), one line per conv on stderr (serialises the stream)
+    if (conv_trace()) {  // debug only (single-threaded use): per-phase timestamps of CTA (0,0,0), one line per conv
       static unsigned long long* dbg = nullptr;
       static unsigned long long last_end = 0;
       if (!dbg) B2_CUDA(cudaMallocManaged(&dbg, 16 * sizeof(unsigned long long)));
@@ -888,15 +891,14 @@ static void hifigan_run(const b200tts_hifigan* m, b200tts_call* c, const float* 
         p.wu = w.wu; p.um_nt = w.nt; p.um_nsplit = w.nsplit;
       };
       const bool umma_rb = m->resblock == 1 && use_umma() && nk == 3 && m->rb[i * nk].c1[0].wu != nullptr &&
-                           !getenv("B200TTS_CONV_TRACE");
+                           !conv_trace();
       // Large stages: run the branches one after the other (branch-major) so the live working set (U + one
       // branch's R/T images) stays inside the 126 MB L2; small stages: one launch covers the three branches so the
       // grid fills the GPU.
-      static long long seq_min = -1;
-      if (seq_min < 0) {
-        const char* e = getenv("B200TTS_RB_SEQ_MIN");
-        seq_min = e ? atoll(e) : (1LL << 40);
-      }
+      static const long long seq_min = [] {
+        const char* e = getenv("B200TTS_RB_SEQ_MIN");  // experiment knob; measured: no gain from branch-major order
+        return e ? atoll(e) : (1LL << 40);
+      }();
       const long long tiles_per_branch = (long long)((L + 127) / 128) * batch * ((cout + 127) / 128);
       const bool batched = umma_rb && tiles_per_branch < seq_min;
       if (umma_rb && !batched) {

@@ -121,3 +121,42 @@ def test_fails_loudly_without_device_or_with_bad_blob():
     assert msg  # either "bad blob magic" (GPU present) or a CUDA error (no device): never a silent fallback
     if ngpu == 0:
         assert "CUDA" in msg
+
+
+def test_bf16_split_images_reconstruct_weights():
+    """umma_image: [n-tile][ci-chunk][tap][plane][4][NT][8]; hi + lo (+ lo2) must reconstruct the fp32 weights."""
+    rs = np.random.RandomState(2)
+    for cout, cin, k, nsplit, nt_max in ((160, 192, 1, 2, 64), (384, 192, 5, 2, 128), (80, 192, 1, 3, 64), (64, 64, 11, 2, 128)):
+        w = rs.standard_normal((cout, cin, k)).astype(np.float32)
+        img, meta = pack.umma_image(w, nsplit, nt_max)
+        nt, ns, nch, kk, ntiles = (int(meta[i]) for i in range(5))
+        assert nt == pack.pick_nt(cout, nt_max) and ns == nsplit and kk == k and nch == (cin + 31) // 32
+        assert nt % 16 == 0 and nt <= nt_max and ntiles * nt >= cout
+        planes = pack.from_bf16_bits(img.reshape(ntiles, nch, k, nsplit, 4, nt, 8))
+        rec = planes.sum(axis=3)  # [ntile][nch][k][4][nt][8]
+        rec = np.transpose(rec, (0, 4, 1, 3, 5, 2)).reshape(ntiles * nt, nch * 32, k)[:cout, :cin]
+        tol = 2.0 ** (-16 if nsplit == 2 else -23) * np.abs(w).max()
+        assert np.abs(rec - w).max() <= tol
+        # padding (channels beyond Cout / Cin) is exactly zero, so garbage x 0 never reaches an accumulator
+        full = np.transpose(planes.sum(axis=3), (0, 4, 1, 3, 5, 2)).reshape(ntiles * nt, nch * 32, k)
+        assert np.all(full[cout:] == 0) and np.all(full[:, cin:] == 0)
+
+
+def test_relative_embedding_image():
+    e = np.random.RandomState(4).standard_normal((9, 96)).astype(np.float32)
+    img = pack.from_bf16_bits(pack.rel_image(e).reshape(3, 12, 16, 8))
+    rec = np.transpose(img.sum(axis=0), (1, 0, 2)).reshape(16, 96)
+    assert np.abs(rec[:9] - e).max() <= 2.0 ** -22 * np.abs(e).max()
+    assert np.all(rec[9:] == 0)
+
+
+def test_pixel_shuffle_conv_equals_conv_transpose():
+    rs = np.random.RandomState(6)
+    for u in (8, 2, 4):
+        k, cin, cout, L = 2 * u, 6, 4, 19
+        w = rs.standard_normal((cin, cout, k)).astype(np.float32)
+        x = rs.standard_normal((1, cin, L)).astype(np.float32)
+        ref = F.conv_transpose1d(torch.from_numpy(x), torch.from_numpy(w), stride=u, padding=(k - u) // 2)[0].numpy()
+        y = F.conv1d(torch.from_numpy(x), torch.from_numpy(pack.pixel_shuffle_conv(w, u, k)), padding=1)[0].numpy()
+        out = y.reshape(cout, u, L).transpose(0, 2, 1).reshape(cout, L * u)  # packed channel n = co*u + r
+        assert np.abs(out - ref).max() < 1e-5

@@ -112,6 +112,28 @@ int b200tts_hifigan_info(const b200tts_hifigan* m, int32_t* mel_channels, int32_
 int b200tts_hifigan_infer(const b200tts_hifigan* m, b200tts_call* call, const float* mel, const int32_t* frames,
                           int batch, int mel_ld, float* pcm_f32, int16_t* pcm_i16, int pcm_ld);
 
+/* ---- spectral-subtraction denoiser (larynx/hifi_gan.py:152-203, STFT of larynx/audio.py:232-306) ---------- */
+/* Strength applied by every following b200tts_hifigan_infer / b200tts_tts_finish on this call (settings key
+ * "denoiser_strength", larynx/hifi_gan.py:152-156; the CLI/server default is 0.005); <= 0 switches it off (default).
+ * On the device: 1024-point Hann STFT with hop 256 over frames 0, 256, ... < N-1024, |X| <- max(|X| - strength*bias, 0)
+ * with the phase kept, windowed inverse FFT, overlap-add without window normalisation — the reference's arithmetic.
+ * pcm_f32 then holds the denoised waveform and pcm_i16 its peak-normalised int16 conversion.  Items of at most 4 mel
+ * frames (N <= 1024) have no STFT frame: the reference returns 1024 zeros for them, this library zero-fills the item. */
+int b200tts_call_set_denoiser(b200tts_call* call, float strength);
+/* The bias spectrum (larynx/hifi_gan.py:181-203): |STFT frame 0| of the vocoder's response to zeros[1][mel][88],
+ * computed on the device when the model is created.  out receives 513 floats (n = capacity of out). */
+int b200tts_hifigan_bias_spectrum(const b200tts_hifigan* m, float* out, int n);
+
+/* HiFiGanVocoder.denoise (larynx/hifi_gan.py:171-179) as a call of its own.  pcm_in [batch][in_ld] float waveforms with
+ * n_samples[b] valid samples; bias (nullable): 513 floats used instead of the model's bias spectrum.  Item b of the outputs
+ * [batch][out_ld] holds n_t*256 + 1024 samples, n_t = number of frame starts 0, 256, ... < n_samples[b] - 1024 (larynx/audio.py:
+ * 232-267; equal to n_samples[b] when that is a multiple of 256 above 1024), zeros beyond.  pcm_f32 / pcm_i16 nullable;
+ * pcm_i16 is audio_float_to_int16 of the denoised item.  strength 0 still runs STFT -> ISTFT (the Hann window is applied twice
+ * and never normalised, exactly like the reference). */
+int b200tts_hifigan_denoise(const b200tts_hifigan* m, b200tts_call* call, float strength, const float* bias,
+                            const float* pcm_in, const int32_t* n_samples, int batch, int in_ld, float* pcm_f32,
+                            int16_t* pcm_i16, int out_ld);
+
 /* ---- fused ids -> PCM (larynx/__init__.py:229-257 without leaving the device) ------------- */
 /* Must follow b200tts_glow_encode on the same call.  Runs decode, the mel glue, the vocoder and
  * the int16 conversion back to back on the call's stream.  mel_out (nullable) receives the

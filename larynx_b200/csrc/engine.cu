@@ -138,6 +138,13 @@ struct b200tts_hifigan {
   int up_rate[8], up_k[8];
   ConvW conv_pre, conv_post, ups[8], ups_ps[8];
   std::vector<HifiRB> rb;  // [n_ups * n_kernels]
+  // denoiser tables (device): numpy.hanning(1024), exp(-2 pi i t / 1024), bias spectrum [513]   larynx/hifi_gan.py:181-203
+  float *dn_hann = nullptr, *dn_tw = nullptr, *dn_bias = nullptr;
+  ~b200tts_hifigan() {
+    cudaFree(dn_hann);
+    cudaFree(dn_tw);
+    cudaFree(dn_bias);
+  }
 };
 
 // host copy of a small fp32 tensor that lives in the device blob
@@ -209,6 +216,7 @@ struct b200tts_call {
   long long launches = 0;
   float last_ms = 0.f;
   int debug = 0;
+  float denoise = 0.f;  // denoiser strength applied after the vocoder (0 = off)           larynx/hifi_gan.py:152-166
   Arena enc, dec, voc, stg;
   // state carried from encode to decode
   const b200tts_glow* enc_model = nullptr;
@@ -760,6 +768,13 @@ static void hifigan_run(const b200tts_hifigan* m, b200tts_call* c, const float* 
   const int Lout_ld = ld0 * hop;
   size_t need = Arena::pad((size_t)B * m->C0 * ld0, 4) + 14 * Arena::pad(B * stage_max, 4) +
                 Arena::pad((size_t)B * Lout_ld, 4) + Arena::pad(B, 4) + Arena::pad((size_t)B * Lout_ld, 2);
+  // denoiser: STFT frames over the longest waveform, windowed inverse frames in scratch
+  const bool dn = c->denoise > 0.f && m->dn_bias != nullptr;
+  const int dn_nt = dn && Tmax * hop > DN_FFT ? (Tmax * hop - DN_FFT + DN_HOP - 1) / DN_HOP : 0;
+  if (dn) {
+    B2_CHECK(hop % DN_HOP == 0, "denoiser expects a vocoder hop that is a multiple of 256");
+    need += Arena::pad((size_t)B * std::max(dn_nt, 1) * DN_FFT, 4);
+  }
   // bf16 operand images: conv_pre output + 7 per stage set (two alternating sets)
   const bool um = use_umma() && m->conv_pre.wu != nullptr && m->C0 % 32 == 0;
   size_t plane_max = 0;
@@ -786,6 +801,7 @@ static void hifigan_run(const b200tts_hifigan* m, b200tts_call* c, const float* 
   }
   unsigned int* peak_d = c->voc.take<unsigned int>(B);
   short* i16_d = c->voc.take<short>((size_t)B * Lout_ld);
+  float* dn_fr = dn ? c->voc.take<float>((size_t)B * std::max(dn_nt, 1) * DN_FFT) : nullptr;
 
   if (Tmax > 0) {
     B2_CUDA(cudaMemsetAsync(peak_d, 0, sizeof(unsigned int) * B, s));
@@ -968,6 +984,19 @@ static void hifigan_run(const b200tts_hifigan* m, b200tts_call* c, const float* 
     launch_conv_post(in1, in2, in3, (long long)cin * Lin_ld, Lin_ld, in_div, 0.01f, m->conv_post.w, m->conv_post.b, cin,
                      m->conv_post.k, frames_d, len_mul, batch, Tmax * len_mul, pcm_d, Lout_ld, peak_d, s);
     c->launches++;
+    if (dn) {
+      // magnitude-domain bias subtraction frame by frame, then overlap-add in place        larynx/hifi_gan.py:171-179
+      const long long fr_bs = (long long)std::max(dn_nt, 1) * DN_FFT;
+      B2_CUDA(cudaMemsetAsync(peak_d, 0, sizeof(unsigned int) * B, s));
+      if (dn_nt > 0) {
+        launch_stft_denoise(pcm_d, Lout_ld, frames_d, len_mul, batch, dn_nt, m->dn_hann, m->dn_tw, m->dn_bias, c->denoise,
+                            dn_fr, fr_bs, nullptr, s);
+        c->launches++;
+      }
+      launch_overlap_add(dn_fr, fr_bs, frames_d, len_mul, batch, std::min(dn_nt * DN_HOP + DN_FFT, Lout_ld), pcm_d, Lout_ld,
+                         peak_d, s);
+      c->launches++;
+    }
     if (pcm_i16) {
       launch_pcm_to_i16(pcm_d, Lout_ld, peak_d, frames_d, len_mul, batch, i16_d, Lout_ld, s);
       c->launches++;
@@ -983,6 +1012,122 @@ static void hifigan_run(const b200tts_hifigan* m, b200tts_call* c, const float* 
   const int w = std::min(pcm_ld, Lout_ld);
   copy_out_2d(pcm_f32, pcm_ld, pcm_d, Lout_ld, batch, w, sizeof(float), s);
   copy_out_2d(pcm_i16, pcm_ld, i16_d, Lout_ld, batch, w, sizeof(short), s);
+}
+
+// Denoiser tables and bias spectrum (larynx/hifi_gan.py:181-203): the bias is the magnitude of the first STFT frame of
+// the vocoder's response to an all-zero mel of 88 frames.  Computed once at model creation so that the model object stays
+// immutable afterwards (the reference initialises it lazily on first use).
+static void hifigan_init_denoiser(b200tts_hifigan* m) {
+  if (m->hop % DN_HOP != 0) return;  // no reference voice has such a vocoder; the denoiser stays unavailable
+  const int dev = m->W.device;
+  B2_CUDA(cudaSetDevice(dev));
+  std::vector<float> hann(DN_FFT), tw(2 * DN_FFT);
+  const double pi = 3.14159265358979323846;
+  for (int n = 0; n < DN_FFT; ++n) {
+    hann[n] = (float)(0.5 - 0.5 * std::cos(2.0 * pi * n / (DN_FFT - 1)));  // numpy.hanning: symmetric window
+    tw[2 * n] = (float)std::cos(2.0 * pi * n / DN_FFT);
+    tw[2 * n + 1] = (float)(-std::sin(2.0 * pi * n / DN_FFT));
+  }
+  B2_CUDA(cudaMalloc(&m->dn_hann, sizeof(float) * DN_FFT));
+  B2_CUDA(cudaMalloc(&m->dn_tw, sizeof(float) * 2 * DN_FFT));
+  B2_CUDA(cudaMemcpy(m->dn_hann, hann.data(), sizeof(float) * DN_FFT, cudaMemcpyHostToDevice));
+  B2_CUDA(cudaMemcpy(m->dn_tw, tw.data(), sizeof(float) * 2 * DN_FFT, cudaMemcpyHostToDevice));
+  const int T = 88, N = T * m->hop;
+  float *mel_d = nullptr, *pcm_d = nullptr, *bias_d = nullptr;
+  int* frames_d = nullptr;
+  b200tts_call* c = nullptr;
+  auto cleanup = [&]() {
+    if (c) b200tts_call_destroy(c);
+    cudaFree(mel_d);
+    cudaFree(pcm_d);
+    cudaFree(frames_d);
+  };
+  try {
+    if (b200tts_call_create(dev, &c) != 0) throw Error(g_err);
+    B2_CUDA(cudaMalloc(&mel_d, sizeof(float) * m->mel * T));
+    B2_CUDA(cudaMalloc(&pcm_d, sizeof(float) * N));
+    B2_CUDA(cudaMalloc(&frames_d, sizeof(int)));
+    B2_CUDA(cudaMalloc(&bias_d, sizeof(float) * DN_BINS));
+    B2_CUDA(cudaMemset(mel_d, 0, sizeof(float) * m->mel * T));
+    B2_CUDA(cudaMemcpy(frames_d, &T, sizeof(int), cudaMemcpyHostToDevice));
+    hifigan_run(m, c, mel_d, T, frames_d, &T, 1, pcm_d, nullptr, N);
+    launch_stft_denoise(pcm_d, N, frames_d, m->hop, 1, 1, m->dn_hann, m->dn_tw, nullptr, 0.f, nullptr, 0, bias_d, c->stream);
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+  } catch (...) {
+    cleanup();
+    cudaFree(bias_d);
+    throw;
+  }
+  cleanup();
+  m->dn_bias = bias_d;
+}
+
+// HiFiGanVocoder.denoise (larynx/hifi_gan.py:171-179) as a call of its own on float waveforms
+static void denoise_impl(const b200tts_hifigan* m, b200tts_call* c, float strength, const float* bias, const float* pcm_in,
+                         const int32_t* n_samples, int batch, int in_ld, float* out_f32, int16_t* out_i16, int out_ld) {
+  B2_CHECK(batch > 0, "empty batch");
+  B2_CHECK(m->W.device == c->device, "model and call live on different devices");
+  B2_CHECK(m->dn_hann != nullptr, "this vocoder has no denoiser (hop is not a multiple of 256)");
+  B2_CHECK(strength >= 0.f, "denoiser strength must be >= 0");
+  B2_CUDA(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  std::vector<int> nh(batch), oh(batch);
+  if (is_device_ptr(n_samples)) B2_CUDA(cudaMemcpy(nh.data(), n_samples, sizeof(int) * batch, cudaMemcpyDeviceToHost));
+  else memcpy(nh.data(), n_samples, sizeof(int) * batch);
+  int nt_max = 0, n_max = 0;
+  for (int b = 0; b < batch; ++b) {
+    B2_CHECK(nh[b] >= 0 && nh[b] <= in_ld, "n_samples[b] out of range");
+    const int nt = nh[b] > DN_FFT ? (nh[b] - DN_FFT + DN_HOP - 1) / DN_HOP : 0;
+    oh[b] = nt * DN_HOP + DN_FFT;
+    nt_max = std::max(nt_max, nt);
+    n_max = std::max(n_max, nh[b]);
+  }
+  const int olen_max = nt_max * DN_HOP + DN_FFT;
+  B2_CHECK(out_ld >= olen_max, "out_ld smaller than the longest denoised item (n_t*256 + 1024)");
+  const long long B = batch;
+  const bool in_dev = is_device_ptr(pcm_in), bias_dev = bias == nullptr || is_device_ptr(bias);
+  const long long fr_bs = (long long)std::max(nt_max, 1) * DN_FFT;
+  c->stg.reserve(2 * Arena::pad(B, 4) + (in_dev ? 0 : Arena::pad((size_t)B * std::max(in_ld, 1), 4)) + Arena::pad(DN_BINS, 4) +
+                 Arena::pad((size_t)B * olen_max, 4) + Arena::pad((size_t)B * fr_bs, 4) + Arena::pad(B, 4) +
+                 Arena::pad((size_t)B * olen_max, 2) + 4096);
+  int* n_d = c->stg.take<int>(B);
+  int* o_d = c->stg.take<int>(B);
+  Timer tm(c);
+  B2_CUDA(cudaMemcpyAsync(n_d, nh.data(), sizeof(int) * B, cudaMemcpyHostToDevice, s));
+  B2_CUDA(cudaMemcpyAsync(o_d, oh.data(), sizeof(int) * B, cudaMemcpyHostToDevice, s));
+  const float* in_d = pcm_in;
+  if (!in_dev) {
+    float* st = c->stg.take<float>((size_t)B * std::max(in_ld, 1));
+    if (in_ld > 0) B2_CUDA(cudaMemcpyAsync(st, pcm_in, sizeof(float) * B * in_ld, cudaMemcpyHostToDevice, s));
+    in_d = st;
+  }
+  const float* bias_d = bias ? bias : m->dn_bias;
+  if (!bias_dev) {
+    float* st = c->stg.take<float>(DN_BINS);
+    B2_CUDA(cudaMemcpyAsync(st, bias, sizeof(float) * DN_BINS, cudaMemcpyHostToDevice, s));
+    bias_d = st;
+  }
+  B2_CHECK(bias_d != nullptr, "no bias spectrum");
+  float* work = c->stg.take<float>((size_t)B * olen_max);
+  float* fr = c->stg.take<float>((size_t)B * fr_bs);
+  unsigned int* peak_d = c->stg.take<unsigned int>(B);
+  short* i16_d = c->stg.take<short>((size_t)B * olen_max);
+  B2_CUDA(cudaMemsetAsync(peak_d, 0, sizeof(unsigned int) * B, s));
+  B2_CUDA(cudaMemsetAsync(work, 0, sizeof(float) * B * olen_max, s));
+  if (nt_max > 0) {
+    launch_stft_denoise(in_d, in_ld, n_d, 1, batch, nt_max, m->dn_hann, m->dn_tw, bias_d, strength, fr, fr_bs, nullptr, s);
+    c->launches++;
+  }
+  launch_overlap_add(fr, fr_bs, n_d, 1, batch, olen_max, work, olen_max, peak_d, s);
+  c->launches++;
+  if (out_i16) {
+    launch_pcm_to_i16(work, olen_max, peak_d, o_d, 1, batch, i16_d, olen_max, s);
+    c->launches++;
+  }
+  copy_out_2d(out_f32, out_ld, work, olen_max, batch, olen_max, sizeof(float), s);
+  copy_out_2d(out_i16, out_ld, i16_d, olen_max, batch, olen_max, sizeof(short), s);
+  tm.stop_and_sync();
+  // the host vectors nh / oh outlive the async copies: stop_and_sync() waited for the stream
 }
 
 static void hifigan_infer_impl(const b200tts_hifigan* m, b200tts_call* c, const float* mel, const int32_t* frames,
@@ -1209,6 +1354,7 @@ int b200tts_hifigan_create(const void* blob, size_t nbytes, int device, b200tts_
   std::unique_ptr<b200tts_hifigan> m(new b200tts_hifigan());
   m->W.load(blob, nbytes, device, 2);
   hifigan_bind(m.get());
+  hifigan_init_denoiser(m.get());
   *out = m.release();
   B2_API_END
 }
@@ -1233,6 +1379,33 @@ int b200tts_hifigan_infer(const b200tts_hifigan* m, b200tts_call* call, const fl
   B2_API_BEGIN
   B2_CHECK(m && call && mel && frames, "null argument");
   hifigan_infer_impl(m, call, mel, frames, batch, mel_ld, pcm_f32, pcm_i16, pcm_ld);
+  B2_API_END
+}
+
+int b200tts_call_set_denoiser(b200tts_call* call, float strength) {
+  B2_API_BEGIN
+  B2_CHECK(call, "null argument");
+  B2_CHECK(strength == strength, "denoiser strength is NaN");
+  call->denoise = strength > 0.f ? strength : 0.f;
+  B2_API_END
+}
+
+int b200tts_hifigan_denoise(const b200tts_hifigan* m, b200tts_call* call, float strength, const float* bias,
+                            const float* pcm_in, const int32_t* n_samples, int batch, int in_ld, float* pcm_f32,
+                            int16_t* pcm_i16, int out_ld) {
+  B2_API_BEGIN
+  B2_CHECK(m && call && pcm_in && n_samples, "null argument");
+  denoise_impl(m, call, strength, bias, pcm_in, n_samples, batch, in_ld, pcm_f32, pcm_i16, out_ld);
+  B2_API_END
+}
+
+int b200tts_hifigan_bias_spectrum(const b200tts_hifigan* m, float* out, int n) {
+  B2_API_BEGIN
+  B2_CHECK(m && out, "null argument");
+  B2_CHECK(m->dn_bias != nullptr, "this vocoder has no denoiser (hop is not a multiple of 256)");
+  B2_CHECK(n >= DN_BINS, "bias spectrum needs room for 513 values");
+  B2_CUDA(cudaSetDevice(m->W.device));
+  B2_CUDA(cudaMemcpy(out, m->dn_bias, sizeof(float) * DN_BINS, cudaMemcpyDefault));
   B2_API_END
 }
 

@@ -654,4 +654,131 @@ void launch_zero_tail(float* y, long long bs, int ld, int C, const int* lens, in
   B2_CUDA(cudaGetLastError());
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Spectral-subtraction denoiser (larynx/hifi_gan.py:171-179) on the device.
+//   transform (larynx/audio.py:291-306):  frames i = 0, 256, ... < N - 1024; X_i = rfft(hanning(1024) * x[i : i + 1024])
+//   denoise:                               |X| <- max(|X| - strength * bias, 0), phase kept
+//   inverse (larynx/audio.py:251-288):    out[i : i + 1024] += hanning(1024) * irfft(X_i); no window-power normalisation
+// One CTA per frame: 1024-point complex FFT (radix-4 Stockham, 5 passes, one butterfly per thread per pass) in shared
+// memory, the per-bin gain max(1 - strength * bias / |X|, 0) applied to bin k and its mirror, and the inverse transform
+// computed as Re(FFT(conj X)) / 1024.  The windowed frames go to a scratch buffer; a second kernel overlap-adds the
+// (up to four) frames that cover each output sample in the reference's order and tracks the peak for the int16
+// conversion — no atomics on the samples, so results are reproducible run to run.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int stft_n_frames(int L) { return L > DN_FFT ? (L - DN_FFT + DN_HOP - 1) / DN_HOP : 0; }
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+
+// forward DFT of a[0..1024); b is scratch; returns the buffer holding the result.  tw[t] = exp(-2 pi i t / 1024).
+__device__ float2* fft1024(float2* a, float2* b, const float2* __restrict__ tw) {
+  const int j = threadIdx.x;
+#pragma unroll
+  for (int Ns = 1; Ns < DN_FFT; Ns *= 4) {
+    const int k = j & (Ns - 1);
+    const int ts = k * (DN_FFT / 4 / Ns);
+    const float2 v0 = a[j];
+    const float2 v1 = cmul(a[j + 256], tw[ts]);
+    const float2 v2 = cmul(a[j + 512], tw[2 * ts]);
+    const float2 v3 = cmul(a[j + 768], tw[3 * ts]);
+    const float2 s02 = make_float2(v0.x + v2.x, v0.y + v2.y), d02 = make_float2(v0.x - v2.x, v0.y - v2.y);
+    const float2 s13 = make_float2(v1.x + v3.x, v1.y + v3.y), d13 = make_float2(v1.x - v3.x, v1.y - v3.y);
+    const int d = ((j - k) << 2) + k;
+    b[d] = make_float2(s02.x + s13.x, s02.y + s13.y);
+    b[d + Ns] = make_float2(d02.x + d13.y, d02.y - d13.x);      // d02 - i d13
+    b[d + 2 * Ns] = make_float2(s02.x - s13.x, s02.y - s13.y);
+    b[d + 3 * Ns] = make_float2(d02.x - d13.y, d02.y + d13.x);  // d02 + i d13
+    __syncthreads();
+    float2* t = a;
+    a = b;
+    b = t;
+  }
+  return a;
+}
+
+// grid (max frames, batch), 256 threads.  mag_out != nullptr: write |X| of frame 0 of item 0 (the bias spectrum,
+// larynx/hifi_gan.py:199-203) instead of denoising.
+__global__ void __launch_bounds__(256) stft_denoise_kernel(const float* __restrict__ pcm, int pcm_ld,
+                                                           const int* __restrict__ frames, int len_mul,
+                                                           const float* __restrict__ hann, const float2* __restrict__ tw,
+                                                           const float* __restrict__ bias, float strength,
+                                                           float* __restrict__ fr, long long fr_bs,
+                                                           float* __restrict__ mag_out) {
+  __shared__ float2 A[DN_FFT], B[DN_FFT];
+  const int b = blockIdx.y, i = blockIdx.x, tid = threadIdx.x;
+  if (i >= stft_n_frames(frames[b] * len_mul)) return;
+  const float* x = pcm + (size_t)b * pcm_ld + (size_t)i * DN_HOP;
+#pragma unroll
+  for (int e = tid; e < DN_FFT; e += 256) A[e] = make_float2(hann[e] * x[e], 0.f);
+  __syncthreads();
+  float2* X = fft1024(A, B, tw);
+  float2* Y = X == A ? B : A;
+  for (int k = tid; k <= DN_FFT / 2; k += 256) {
+    const float2 v = X[k];
+    const float m = sqrtf(v.x * v.x + v.y * v.y);
+    if (mag_out) {
+      mag_out[k] = m;
+      continue;
+    }
+    const float g = m > 0.f ? fmaxf(m - strength * bias[k], 0.f) / m : 0.f;
+    const float re = v.x * g, im = v.y * g;
+    if (k == 0 || k == DN_FFT / 2) {
+      Y[k] = make_float2(re, 0.f);  // irfft ignores the imaginary part of DC and Nyquist
+    } else {
+      Y[k] = make_float2(re, -im);  // conj(X): the inverse transform is Re(FFT(conj X)) / N
+      Y[DN_FFT - k] = make_float2(re, im);
+    }
+  }
+  if (mag_out) return;
+  __syncthreads();
+  const float2* Z = fft1024(Y, X, tw);
+  float* o = fr + (size_t)b * fr_bs + (size_t)i * DN_FFT;
+#pragma unroll
+  for (int e = tid; e < DN_FFT; e += 256) o[e] = hann[e] * (Z[e].x * (1.0f / DN_FFT));
+}
+
+// overlap-add (larynx/audio.py:262-267): out[n] = sum over frames i covering n, i ascending; peak for audio_float_to_int16
+__global__ void __launch_bounds__(256) overlap_add_kernel(const float* __restrict__ fr, long long fr_bs,
+                                                          const int* __restrict__ frames, int len_mul,
+                                                          float* __restrict__ pcm, int pcm_ld,
+                                                          unsigned int* __restrict__ peak_bits) {
+  const int b = blockIdx.y;
+  const int n = blockIdx.x * 256 + threadIdx.x;
+  const int nt = stft_n_frames(frames[b] * len_mul);
+  const int olen = nt * DN_HOP + DN_FFT;
+  float av = 0.f;
+  if (n < olen && n < pcm_ld) {
+    const int blk = n / DN_HOP;
+    const float* f = fr + (size_t)b * fr_bs;
+    float v = 0.f;
+#pragma unroll
+    for (int j = DN_FFT / DN_HOP - 1; j >= 0; --j) {
+      const int i = blk - j;
+      if (i >= 0 && i < nt) v += f[(size_t)i * DN_FFT + (n - i * DN_HOP)];
+    }
+    pcm[(size_t)b * pcm_ld + n] = v;
+    av = fabsf(v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) av = fmaxf(av, __shfl_xor_sync(0xffffffffu, av, o));
+  if ((threadIdx.x & 31) == 0 && av > 0.f) atomicMax(peak_bits + b, __float_as_uint(av));
+}
+
+void launch_stft_denoise(const float* pcm, int pcm_ld, const int* frames, int len_mul, int batch, int max_frames,
+                         const float* hann, const float* tw, const float* bias, float strength, float* fr,
+                         long long fr_bs, float* mag_out, cudaStream_t s) {
+  if (max_frames <= 0 || batch <= 0) return;
+  dim3 grid(max_frames, batch);
+  stft_denoise_kernel<<<grid, 256, 0, s>>>(pcm, pcm_ld, frames, len_mul, hann, (const float2*)tw, bias, strength, fr, fr_bs,
+                                           mag_out);
+  B2_CUDA(cudaGetLastError());
+}
+
+void launch_overlap_add(const float* fr, long long fr_bs, const int* frames, int len_mul, int batch, int max_len,
+                        float* pcm, int pcm_ld, unsigned int* peak_bits, cudaStream_t s) {
+  if (max_len <= 0 || batch <= 0) return;
+  dim3 grid((max_len + 255) / 256, batch);
+  overlap_add_kernel<<<grid, 256, 0, s>>>(fr, fr_bs, frames, len_mul, pcm, pcm_ld, peak_bits);
+  B2_CUDA(cudaGetLastError());
+}
+
 }  // namespace b2

@@ -46,4 +46,14 @@ void launch_pcm_to_i16(const float* pcm, int pcm_ld, const unsigned int* peak_bi
 void launch_zero_tail(float* y, long long bs, int ld, int C, const int* lens, int len_mul, int batch, int width,
                       cudaStream_t s);
 
+// spectral-subtraction denoiser (larynx/hifi_gan.py:171-179; STFT constants larynx/audio.py:232-249)
+constexpr int DN_FFT = 1024, DN_HOP = 256, DN_BINS = DN_FFT / 2 + 1;
+// tw: 1024 (cos, sin) pairs of exp(-2 pi i t / 1024); hann: numpy.hanning(1024); fr: scratch [batch][fr_bs] floats,
+// fr_bs >= max_frames * 1024.  mag_out != nullptr: only write |X| (513 values) of frame 0 of item 0.
+void launch_stft_denoise(const float* pcm, int pcm_ld, const int* frames, int len_mul, int batch, int max_frames,
+                         const float* hann, const float* tw, const float* bias, float strength, float* fr,
+                         long long fr_bs, float* mag_out, cudaStream_t s);
+void launch_overlap_add(const float* fr, long long fr_bs, const int* frames, int len_mul, int batch, int max_len,
+                        float* pcm, int pcm_ld, unsigned int* peak_bits, cudaStream_t s);
+
 }  // namespace b2

@@ -55,6 +55,10 @@ class Call:
     def set_debug(self, on: bool):
         check(_lib.load().b200tts_call_set_debug(self._h, int(on)))
 
+    def set_denoiser(self, strength: float):
+        """Denoiser strength of the following vocoder calls on this context (0 = off; larynx/hifi_gan.py:152-166)."""
+        check(_lib.load().b200tts_call_set_denoiser(self._h, float(strength)))
+
 
 class _CallPool:
     """One Call per (host thread, device): `_sentence_task` runs on ThreadPoolExecutor workers against
@@ -153,6 +157,17 @@ class HifiGanModel:
             self.close()
         except Exception:  # noqa: BLE001
             pass
+
+    def bias_spectrum(self) -> np.ndarray:
+        """Denoiser bias spectrum [513] (larynx/hifi_gan.py:181-203), computed on the device at model creation."""
+        out = np.zeros(513, dtype=np.float32)
+        check(_lib.load().b200tts_hifigan_bias_spectrum(self._h, ptr(out), 513))
+        return out
+
+    def denoise(self, call: Call, strength: float, pcm_in, n_samples, batch: int, in_ld: int, pcm_f32=None, pcm_i16=None,
+                out_ld: int = 0, bias=None):
+        check(_lib.load().b200tts_hifigan_denoise(self._h, call._h, float(strength), ptr(bias), ptr(pcm_in), ptr(n_samples), batch,
+                                                  int(in_ld), ptr(pcm_f32), ptr(pcm_i16), int(out_ld)))
 
     def infer(self, call: Call, mel, frames, batch: int, mel_ld: int, pcm_f32=None, pcm_i16=None, pcm_ld: int = 0):
         check(_lib.load().b200tts_hifigan_infer(self._h, call._h, ptr(mel), ptr(frames), batch, int(mel_ld), ptr(pcm_f32), ptr(pcm_i16), int(pcm_ld)))

@@ -82,9 +82,11 @@ def sentence_task(phoneme_ids, glue: MelGlue, tts_model, tts_settings, vocoder_m
 
 def synthesize_batch(tts_model, vocoder_model, glue: MelGlue, id_rows: Sequence[np.ndarray], noise_scale: float = 0.667,
                      length_scale: float = 1.0, eps: Optional[np.ndarray] = None, seed: int = 0, want_mel: bool = False,
-                     want_float: bool = False):
+                     want_float: bool = False, denoiser_strength: float = 0.0):
     """Fused path: ids -> PCM for a ragged batch without leaving the device between the passes
-    (b200tts_glow_encode + b200tts_tts_finish).  Returns a list of int16 arrays (+ mels / float pcm)."""
+    (b200tts_glow_encode + b200tts_tts_finish).  Returns a list of int16 arrays (+ mels / float pcm).
+    `denoiser_strength` > 0 runs the spectral-subtraction denoiser (larynx/hifi_gan.py:158-179) on the device
+    after the vocoder, per item."""
     g, v = tts_model.model, vocoder_model.model
     call = engine.CALLS.get(g.device)
     ids, x_len = engine.pad_ids(id_rows)
@@ -100,11 +102,22 @@ def synthesize_batch(tts_model, vocoder_model, glue: MelGlue, id_rows: Sequence[
         eps = np.ascontiguousarray(eps, dtype=np.float32)
         assert eps.ndim == 3 and eps.shape[0] == b and eps.shape[2] >= ty
         eps_ld = eps.shape[2]
-    engine.tts_finish(g, v, call, glue.c_struct(), noise_scale, eps, eps_ld, seed, mel, mel.shape[2] if want_mel else 0,
-                      pcm_f32, pcm_i16, pcm_i16.shape[1])
-    out = {"audio": [pcm_i16[i, : int(y_len[i]) * v.hop] for i in range(b)], "y_len": y_len}
+    call.set_denoiser(denoiser_strength)
+    try:
+        engine.tts_finish(g, v, call, glue.c_struct(), noise_scale, eps, eps_ld, seed, mel, mel.shape[2] if want_mel else 0,
+                          pcm_f32, pcm_i16, pcm_i16.shape[1])
+    finally:
+        call.set_denoiser(0.0)
+
+    def item(buf, i):
+        n = int(y_len[i]) * v.hop
+        if denoiser_strength > 0 and 0 < n <= 1024:  # no STFT frame fits: the reference returns 1024 zeros
+            return np.zeros(1024, dtype=buf.dtype)
+        return buf[i, :n]
+
+    out = {"audio": [item(pcm_i16, i) for i in range(b)], "y_len": y_len}
     if want_mel:
         out["mel"] = [mel[i, :, : int(y_len[i])] for i in range(b)]
     if want_float:
-        out["pcm"] = [pcm_f32[i, : int(y_len[i]) * v.hop] for i in range(b)]
+        out["pcm"] = [item(pcm_f32, i) for i in range(b)]
     return out

@@ -1,4 +1,8 @@
-"""Spectral-subtraction denoiser of the vocoder boundary (host side, numpy — as in the reference).
+"""TEST INFRASTRUCTURE — vectorised numpy restatement of the reference's spectral-subtraction denoiser.
+
+Only tests/ may import this module (like everything under oracle/); the product path runs the denoiser on the
+device (larynx_b200/csrc/kernels.cu, stft_denoise_kernel / overlap_add_kernel).  Pinned against the reference's
+own `larynx.audio.transform` / `inverse` in tests/test_oracle_pinned.py and tests/golden/denoiser.npz.
 
 Mirrors `HiFiGanVocoder.denoise` / `maybe_init_denoiser` (larynx/hifi_gan.py:171-203) and the STFT helpers
 `transform` / `inverse` / `stft` / `istft` (larynx/audio.py:232-306): 1024-point periodic-less `np.hanning`
@@ -7,7 +11,8 @@ overlap-add of the windowed inverse FFT *without* window-power normalisation (th
 peak normalisation of `audio_float_to_int16` absorbs the gain), spectrum rounded through complex64 exactly where
 the reference does (`larynx/audio.py:275-277`).
 
-The reference runs this in per-frame Python loops on the host; here the same arithmetic is vectorised over frames.
+The reference runs this in per-frame Python loops on the host; here the same arithmetic is vectorised over frames
+(oracle/port.py:denoise_reference keeps the loop form).
 The bias spectrum is the first STFT frame of the vocoder's response to an all-zero mel of 88 frames.
 """
 from __future__ import annotations
@@ -69,6 +74,6 @@ def denoise(audio: np.ndarray, bias_spec: np.ndarray, strength: float) -> np.nda
 
 
 def audio_float_to_int16(audio: np.ndarray, max_wav_value: float = 32767.0) -> np.ndarray:
-    """larynx/audio.py:118-125 (host mirror, used after the host denoiser)."""
+    """larynx/audio.py:118-125."""
     a = audio * (max_wav_value / max(0.01, np.max(np.abs(audio))))
     return np.clip(a, -max_wav_value, max_wav_value).astype("int16")

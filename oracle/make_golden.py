@@ -110,5 +110,45 @@ def main():
         print(name, "pcm std", float(pcm.std()), "absmax", float(np.abs(pcm).max()))
 
 
+    make_denoiser(gen, a["mel_glued"], outdir)
+
+
+def make_denoiser(gen, mel_glued, outdir):
+    """Golden vectors of the spectral-subtraction denoiser made by the reference's own numpy STFT code
+    (larynx/audio.py:232-306) in the order larynx/hifi_gan.py:158-203 applies it."""
+    ref_harness.import_reference()
+    import larynx.audio as la
+
+    # (1) pure STFT arithmetic on random input with a strong bias (many clipped bins)
+    rs = np.random.RandomState(3)
+    audio = (rs.randn(1, 256 * 41) * 0.3).astype(np.float32)
+    bias = np.abs(rs.randn(1, 513, 1)) * 0.5
+    m, p = la.transform(audio)
+    out = la.inverse(np.clip(m - bias * 0.7, a_min=0.0, a_max=None), p)
+    # (2) the CLI default on the fixture-28 utterance: bias from the vocoder on zeros[1, 80, 88], strength 0.005
+    with torch.no_grad():
+        bias_audio = gen(torch.zeros(1, 80, 88)).squeeze(0).numpy()
+        pcm = gen(torch.from_numpy(mel_glued[None])).squeeze(0).numpy()
+    bias_spec, _ = la.transform(bias_audio)
+    bias_spec = bias_spec[:, :, 0][:, :, None]
+    m, p = la.transform(pcm)
+    pcm_dn = la.inverse(np.clip(m - bias_spec * 0.005, a_min=0.0, a_max=None), p)
+    np.savez_compressed(outdir / "denoiser.npz", audio=audio, bias=bias, strength=np.array(0.7), out=out,
+                        fixture28_bias_spec=bias_spec.astype(np.float32), fixture28_strength=np.array(0.005),
+                        fixture28_pcm_denoised=pcm_dn.astype(np.float32).reshape(-1),
+                        fixture28_audio_denoised=la.audio_float_to_int16(pcm_dn).squeeze())
+    print("denoiser: bias max", float(bias_spec.max()), "pcm_dn absmax", float(np.abs(pcm_dn).max()))
+
+
 if __name__ == "__main__":
-    main()
+    import sys
+
+    if "--denoiser-only" in sys.argv:
+        _tmp = Path(tempfile.mkdtemp())
+        synth.write_glow_voice(_tmp / "glow", 46, GLOW_SEED)
+        synth.write_hifigan_voice(_tmp / "hifi", "universal_large", HIFI_SEED)
+        _, _gen = ref_harness.load_reference_models(_tmp / "glow", _tmp / "hifi")
+        _g = np.load(ROOT / "tests" / "golden" / "ljspeech_fixture28.npz")
+        make_denoiser(_gen, _g["mel_glued"], ROOT / "tests" / "golden")
+    else:
+        main()

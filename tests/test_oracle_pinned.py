@@ -119,10 +119,11 @@ def test_reference_batched_equals_single():
     assert float(both["mel"][0, :, ty:].abs().max()) == 0.0
 
 
-def test_denoiser_product_equals_oracle_and_reference():
-    """larynx_b200/denoise.py (vectorised host mirror) vs the loop-form restatement, and vs the reference's own
-    transform/inverse (larynx/audio.py:270-306) where it can be imported."""
-    from larynx_b200 import denoise
+def test_denoiser_restatements_equal_reference():
+    """Loop-form (oracle/port.py) and vectorised (oracle/denoise_np.py) restatements of the denoiser agree with each
+    other, with the committed golden vector (made by the reference's own larynx.audio.transform / inverse) and with
+    those functions themselves where the reference can be imported."""
+    from oracle import denoise_np as denoise
 
     rs = np.random.RandomState(3)
     audio = (rs.randn(1, 256 * 41) * 0.3).astype(np.float32)
@@ -133,6 +134,9 @@ def test_denoiser_product_equals_oracle_and_reference():
     assert np.abs(a - b).max() < 1e-12
     assert np.array_equal(denoise.audio_float_to_int16(a), port.float_to_int16(b))
     assert denoise.denoise(np.zeros((1, 300), np.float32), bias, 0.5).shape == (1, 1024)  # shorter than one frame
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "denoiser.npz"))
+    for fn in (denoise.denoise, port.denoise_reference):
+        assert np.abs(fn(g["audio"], g["bias"], float(g["strength"])) - g["out"]).max() < 1e-12
     if ref_harness.available():
         ref_harness.import_reference()
         import larynx.audio as la

@@ -91,6 +91,12 @@ struct ConvParams {
   long long yp_bs = 0;
   int yp_kc = 0, yp_rows = 0, yp_nsplit = 2;
   float yp_slope = 1.f;  // planes hold v > 0 ? v : v*slope (the consumer's LeakyReLU); 1 = identity
+  // residual read from a 2-plane bf16 image instead of fp32 `res` (EPI_PLAIN): res = unlrelu(hi + lo), i.e. the image
+  // of the tensor this block started from; may alias yp (each thread reads its elements before it rewrites them)
+  const void* rp = nullptr;
+  long long rp_bs = 0;
+  int rp_kc = 0, rp_rows = 0;
+  float rp_inv_slope = 1.f;  // 1 / slope of the LeakyReLU the image was stored with
 };
 
 // up to three independent convs of identical output geometry in ONE launch (the three MRF ResBlock branches of a

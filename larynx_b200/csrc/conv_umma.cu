@@ -13,7 +13,9 @@ static void set_attr_umma() {
 
 // kernel variants (MT, NSPLIT, EW, WST, AST, G)
 #define UMMA_BIG 1, 2, 8, 3, 2, 1        /* large grids: two CTAs per SM */
-#define UMMA_BIG2 2, 2, 8, 6, 2, 1       /* 256-row tiles (kept for experiments) */
+#define UMMA_BIG2 2, 2, 8, 3, 2, 1       /* 256-row tiles, NT <= 64 (HiFi-GAN stage 3): half the weight traffic and per-CTA set-up, still two CTAs per SM */
+#define UMMA_TALL128 2, 2, 16, 8, 2, 1    /* experiment: 256-row tiles at NT = 128, whole SM (TMEM 512 columns), deep weight ring */
+#define UMMA_BIG4 4, 2, 8, 3, 1, 1       /* 512-row tiles, NT <= 32 and one input chunk (stage 4) */
 #define UMMA_SMALL128 1, 2, 16, 3, 2, 2  /* small grids, NT = 128: 2 taps (32 KB) per weight slot */
 #define UMMA_SMALL64 1, 2, 16, 3, 3, 5   /* small grids, NT <= 64: up to 5 taps (40 KB) per slot, 3 activation stages */
 #define UMMA_ENC128 1, 3, 16, 3, 2, 1    /* 3-way split (text encoder) */
@@ -22,6 +24,8 @@ static void set_attr_umma() {
 void conv_umma_init_attributes() {
   set_attr_umma<UMMA_BIG>();
   set_attr_umma<UMMA_BIG2>();
+  set_attr_umma<UMMA_BIG4>();
+  set_attr_umma<UMMA_TALL128>();
   set_attr_umma<UMMA_SMALL128>();
   set_attr_umma<UMMA_SMALL64>();
   set_attr_umma<UMMA_ENC128>();
@@ -31,6 +35,12 @@ void conv_umma_init_attributes() {
 template <int MT, int NSPLIT, int EW, int WST, int AST, int G>
 static void launch_umma_cfg(const ConvBatch& pb, int batch, int Lmax, cudaStream_t s) {
   const ConvParams& p = pb.p[0];
+  for (int i = 0; i < pb.n; ++i) {  // images are sized for whole tiles of this variant
+    const ConvParams& q = pb.p[i];
+    const int Lr = (Lmax + MT * 128 - 1) / (MT * 128) * (MT * 128);
+    if (q.xp) B2_CHECK(q.xp_rows >= UM_PADL + Lr + UM_HALO, "conv_umma: input plane image too short");
+    if (q.yp) B2_CHECK(q.yp_rows >= UM_PADL + Lr * (q.pix > 1 ? q.pix : 1) + UM_TAIL, "conv_umma: output plane image too short");
+  }
   const size_t smem = UmmaCfg<MT>::smem_bytes(NSPLIT, p.um_nt, WST, AST, G);
   B2_CHECK(smem <= 227 * 1024, "conv_umma: shared memory budget exceeded");
   const int ntiles = (p.Cout + p.um_nt - 1) / p.um_nt;
@@ -59,14 +69,7 @@ int launch_conv_umma_batch(const ConvParams* ps, int n, int batch, int Lmax, cud
     B2_CHECK((p.K - 1) * p.dil <= UM_HALO, "conv_umma: receptive field too wide");
     B2_CHECK(p.pad_left <= UM_PADL, "conv_umma: left padding too wide");
     B2_CHECK(p.n_phase == 1, "conv_umma: transposed convs are packed as pixel-shuffle convs");
-    if (p.xp) {
-      B2_CHECK(p.xp_kc >= (p.Cin + 31) / 32 * 4, "conv_umma: input plane image too narrow");
-      B2_CHECK(p.xp_rows >= UM_PADL + (Lmax + 127) / 128 * 128 + UM_HALO, "conv_umma: input plane image too short");
-    }
-    if (p.yp) {
-      const int u = p.pix > 1 ? p.pix : 1;
-      B2_CHECK(p.yp_rows >= UM_PADL + ((Lmax + 127) / 128 * 128) * u + UM_TAIL, "conv_umma: output plane image too short");
-    }
+    if (p.xp) B2_CHECK(p.xp_kc >= (p.Cin + 31) / 32 * 4, "conv_umma: input plane image too narrow");
     B2_CHECK(p.Cout == ps[0].Cout && p.um_nt == ps[0].um_nt && p.um_nsplit == ps[0].um_nsplit && p.Cin == ps[0].Cin,
              "conv_umma: convs of one launch must share their geometry");
     pb.p[i] = p;
@@ -75,15 +78,20 @@ int launch_conv_umma_batch(const ConvParams* ps, int n, int batch, int Lmax, cud
   const ConvParams& p = ps[0];
   const int ntiles = (p.Cout + p.um_nt - 1) / p.um_nt;
   const long long ctas1 = (long long)((Lmax + 127) / 128) * ntiles * batch * n;
-  const long long ctas2 = (long long)((Lmax + 255) / 256) * ntiles * batch * n;
-  // tuning knobs (thread-safe one-time init); measured: two co-resident 128-row CTAs per SM beat one 256-row CTA
-  static const long long mt2_min = [] { const char* e = getenv("B200TTS_MT2_MIN"); return e ? atoll(e) : (1LL << 40); }();
+  // tuning knobs (thread-safe one-time init).  Narrow layers with very many time tiles (HiFi-GAN stages 3 and 4) are
+  // bound by per-CTA set-up and by re-streaming the weights for every 128 rows: taller tiles amortise both.
+  static const long long mt_min = [] { const char* e = getenv("B200TTS_MT_MIN"); return e ? atoll(e) : 1184LL; }();
+  static const long long tall128_min = [] { const char* e = getenv("B200TTS_TALL128_MIN"); return e ? atoll(e) : (1LL << 40); }();
   static const long long ew16_max = [] { const char* e = getenv("B200TTS_EW16_MAX"); return e ? atoll(e) : 148LL; }();
   if (p.um_nsplit == 3) {
     if (p.um_nt <= 64) launch_umma_cfg<UMMA_ENC64>(pb, batch, Lmax, stream);
     else launch_umma_cfg<UMMA_ENC128>(pb, batch, Lmax, stream);
-  } else if (ctas2 >= mt2_min) {
+  } else if (ctas1 >= mt_min && p.um_nt <= 32 && p.Cin <= 32) {
+    launch_umma_cfg<UMMA_BIG4>(pb, batch, Lmax, stream);
+  } else if (ctas1 >= mt_min && p.um_nt <= 64) {
     launch_umma_cfg<UMMA_BIG2>(pb, batch, Lmax, stream);
+  } else if (ctas1 >= tall128_min && p.um_nt == 128) {
+    launch_umma_cfg<UMMA_TALL128>(pb, batch, Lmax, stream);
   } else if (ctas1 > ew16_max) {
     launch_umma_cfg<UMMA_BIG>(pb, batch, Lmax, stream);
   } else if (p.um_nt <= 64) {

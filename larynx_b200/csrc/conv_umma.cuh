@@ -37,7 +37,7 @@ constexpr int UM_PADL = 40;              // zero rows in front of a plane image 
 constexpr int UM_TAIL = 128;             // zero rows written behind the last tile (>= UM_HALO)
 
 // rows (per 8-channel group) a plane image must provide for a tensor of max length L
-__host__ __device__ inline int um_plane_rows(int L) { return UM_PADL + (L + 255) / 256 * 256 + UM_TAIL + 128; }
+__host__ __device__ inline int um_plane_rows(int L) { return UM_PADL + (L + 511) / 512 * 512 + UM_TAIL + 128; }
 
 template <int MT>
 struct UmmaCfg {
@@ -164,7 +164,7 @@ __device__ __forceinline__ void plane_store4(const PlaneOut& po, int kc, int bof
 // AST: activation ring depth (per 32-channel chunk); G: conv taps per weight stage (one bulk copy, one wait, one
 // commit per stage — the single MMA-issuing warp is the serial resource of the main loop, so fewer, fatter stages).
 template <int MT, int NSPLIT, int EW, int WST, int AST, int G>
-__global__ void __launch_bounds__(EW * 32 + 64, (MT == 1 && EW == 8) ? 2 : 1) conv_umma_kernel(const __grid_constant__ ConvBatch pb) {
+__global__ void __launch_bounds__(EW * 32 + 64, EW == 8 ? 2 : 1) conv_umma_kernel(const __grid_constant__ ConvBatch pb) {
   using namespace umma;
   const ConvParams& p = pb.p[blockIdx.z / pb.zb];
   using C = UmmaCfg<MT>;
@@ -327,17 +327,19 @@ __global__ void __launch_bounds__(EW * 32 + 64, (MT == 1 && EW == 8) ? 2 : 1) co
       if (tid == 0) {
         const unsigned char* xp = reinterpret_cast<const unsigned char*>(p.xp) + (size_t)b * p.xp_bs;
         const long long row0 = (long long)t0 - p.pad_left + UM_PADL;
+        // only the rows the taps can reach: MT*128 + (K-1)*dil of the RA rows a stage has room for
+        const uint32_t kc_bytes = (uint32_t)(MT * 128 + (K - 1) * dil) * 16;
         int as = 0;
         uint32_t aph = 1;
         for (int c = 0; c < nch; ++c, as = (as + 1 == AST ? 0 : as + 1), aph ^= (as == 0)) {
           mbar_wait(&a_empty[as], aph);
-          mbar_arrive_expect_tx(&a_full[as], a_stage);
+          mbar_arrive_expect_tx(&a_full[as], NSPLIT * UM_KCH * kc_bytes);
           unsigned char* dst = sA + (size_t)as * a_stage;
           for (int sp = 0; sp < NSPLIT; ++sp)
 #pragma unroll
             for (int kc = 0; kc < UM_KCH; ++kc)
               bulk_g2s(dst + sp * a_split_bytes + kc * RA * 16,
-                       xp + (((size_t)sp * p.xp_kc + c * UM_KCH + kc) * p.xp_rows + row0) * 16, RA * 16, &a_full[as]);
+                       xp + (((size_t)sp * p.xp_kc + c * UM_KCH + kc) * p.xp_rows + row0) * 16, kc_bytes, &a_full[as]);
           if (c == 0) UM_TRACE(2);
           if (c == nch - 1) UM_TRACE(5);
         }
@@ -420,27 +422,27 @@ __global__ void __launch_bounds__(EW * 32 + 64, (MT == 1 && EW == 8) ? 2 : 1) co
     tc_fence_after();
     if (tid == 0) UM_TRACE(6);
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
-    const int wset = warp >> 2; // EW/4 warp sets share the (M tile, column group) work
-    const int mt = MT == 2 ? (wset & 1) : 0;
-    const int cset = MT == 2 ? (wset >> 1) : wset;       // column-group residue owned by this warp set
-    constexpr int NCSET = MT == 2 ? EW / 8 : EW / 4;
+    const int wset = warp >> 2; // EW/4 warp sets share the (M tile, 32-column group) tasks round robin
+    constexpr int NWS = EW / 4;
     const int m = quad * 32 + lane;
-    const int t = t0 + mt * 128 + m;
-    const bool t_ok = t < Lb;
     const int ngroups = (NT + 31) / 32;
     const int u = p.pix > 1 ? p.pix : 1;
     // plane outputs: primary (yp) and, for EPI_RESSKIP, the skip accumulator (yp2)
     PlaneOut po, po2;
     po.base = p.yp ? reinterpret_cast<unsigned char*>(p.yp) + (size_t)b * p.yp_bs : nullptr;
     po.kc_total = p.yp_kc; po.rows = p.yp_rows; po.nsplit = p.yp_nsplit; po.slope = p.yp_slope;
-    po.pad_front = blockIdx.x == 0;
-    po.pad_tail = (long long)(t0 + MT * 128) >= Lb;
-    po.m = mt * 128 + m;
     po.tail_row0 = (long long)UM_PADL + (long long)(t0 + MT * 128) * u;
-    po2 = po;
-    po2.base = p.yp2 ? reinterpret_cast<unsigned char*>(p.yp2) + (size_t)b * p.yp_bs : nullptr;
 
-    for (int g = cset; g < ngroups; g += NCSET) {
+    for (int task = wset; task < MT * ngroups; task += NWS) {
+      const int mt = MT == 1 ? 0 : task % MT;  // task = g * MT + mt
+      const int g = MT == 1 ? task : task / MT;
+      const int t = t0 + mt * 128 + m;
+      const bool t_ok = t < Lb;
+      po.pad_front = blockIdx.x == 0;
+      po.pad_tail = (long long)(t0 + MT * 128) >= Lb;
+      po.m = mt * 128 + m;
+      po2 = po;
+      po2.base = p.yp2 ? reinterpret_cast<unsigned char*>(p.yp2) + (size_t)b * p.yp_bs : nullptr;
       float acc[32];
       {
         uint32_t raw[32];
@@ -460,11 +462,30 @@ __global__ void __launch_bounds__(EW * 32 + 64, (MT == 1 && EW == 8) ? 2 : 1) co
       const int nb = n0 + g * 32;  // packed channel of acc[0]
       const int jmax = min(32, min(NT - g * 32, p.Cout - nb));
       if (jmax <= 0) continue;
-      if (tid == 0 && g == cset) UM_TRACE(9);
+      if (tid == 0 && task == wset) UM_TRACE(9);
       if (p.epi == EPI_PLAIN && u == 1) {
         float* __restrict__ yb = p.y + (size_t)b * p.y_bs + t;
         float rv[32];
-        if (p.res && t_ok) {
+        if (p.rp) {
+          // residual from the hi/lo image of the block input (16 significant bits; 8 channels per 16-byte load)
+          const unsigned char* rb = reinterpret_cast<const unsigned char*>(p.rp) + (size_t)b * p.rp_bs;
+          const size_t pstride = (size_t)p.rp_kc * p.rp_rows * 16;
+          const long long row = (long long)UM_PADL + (t_ok ? t : 0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int kc = (nb >> 3) + (q * 8 < jmax ? q : 0);
+            const unsigned char* a = rb + ((size_t)kc * p.rp_rows + row) * 16;
+            const uint4 h = *reinterpret_cast<const uint4*>(a), l = *reinterpret_cast<const uint4*>(a + pstride);
+            const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float v0 = __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
+              const float v1 = __uint_as_float(hw[e] & 0xffff0000u) + __uint_as_float(lw[e] & 0xffff0000u);
+              rv[q * 8 + 2 * e] = v0 > 0.f ? v0 : v0 * p.rp_inv_slope;
+              rv[q * 8 + 2 * e + 1] = v1 > 0.f ? v1 : v1 * p.rp_inv_slope;
+            }
+          }
+        } else if (p.res && t_ok) {
           const float* __restrict__ rb = p.res + (size_t)b * p.res_bs + t;
 #pragma unroll
           for (int j = 0; j < 32; ++j) rv[j] = rb[(size_t)(nb + (j < jmax ? j : 0)) * p.res_ld];
@@ -603,13 +624,13 @@ __global__ void __launch_bounds__(EW * 32 + 64, (MT == 1 && EW == 8) ? 2 : 1) co
         }
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc[j] = (t_ok && j < jmax) ? old[j] + (acc[j] + s_bias[g * 32 + j]) : 0.f;
-        if (tid == 0 && g == cset) UM_TRACE(10);
+        if (tid == 0 && task == wset) UM_TRACE(10);
         if (t_ok) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (j < jmax) db[(size_t)j * ld] = acc[j];
         }
-        if (tid == 0 && g == cset) UM_TRACE(11);
+        if (tid == 0 && task == wset) UM_TRACE(11);
         const PlaneOut& pp = in_y ? po : po2;
         if (pp.base) {
           const int c0 = in_y ? nb : nb - p.split;

@@ -269,7 +269,7 @@ struct Planes {
   long long bs = 0;  // bytes per batch item
   int kc = 0, rows = 0, nsplit = 2;
 };
-static int plane_rows(int Lin_max, int u) { return 40 + (Lin_max + 255) / 256 * 256 * u + 256; }
+static int plane_rows(int Lin_max, int u) { return 40 + (Lin_max + 511) / 512 * 512 * u + 256; }  // whole 512-row tiles + tail
 static size_t plane_item_bytes(int channels, int rows, int nsplit) { return (size_t)nsplit * ((channels + 31) / 32 * 4) * rows * 16; }
 static Planes take_planes(Arena& a, int batch, int channels, int rows, int nsplit) {
   Planes pl;
@@ -295,6 +295,10 @@ static bool use_umma() {
     const char* e = getenv("B200TTS_CONV");
     return !(e && strcmp(e, "simt") == 0);
   }();
+  return on;
+}
+static bool res_from_planes() {
+  static const bool on = getenv("B200TTS_RES_FP32") == nullptr;
   return on;
 }
 static bool conv_trace() {
@@ -900,6 +904,14 @@ static void hifigan_run(const b200tts_hifigan* m, b200tts_call* c, const float* 
         if (planes) {
           set_in(q, T_p[j]);
           if (d + 1 < r.ndil) set_out(q, R_p[j], 0.1f);
+          if (res_from_planes()) {
+            // the block input already exists as a hi/lo image (c1's operand): read the residual from it and keep the
+            // fp32 copy of x only where a non-MMA consumer needs it (last dilation: upsampler gather / conv_post)
+            const Planes& rpl = d == 0 ? U_p : R_p[j];
+            q.rp = rpl.ptr; q.rp_bs = rpl.bs; q.rp_kc = rpl.kc; q.rp_rows = rpl.rows; q.rp_inv_slope = 10.f;
+            q.res = nullptr;
+            if (d + 1 < r.ndil) q.y = nullptr;
+          }
         }
       };
       auto bind = [&](ConvParams& p, const ConvW& w) {

@@ -104,6 +104,7 @@ struct ConvParams {
 struct ConvBatch {
   int n = 1;
   int zb = 1;  // batch items per branch
+  int gx[3] = {0, 0, 0};  // persistent launches: CTAs (along x) that share the time tiles of branch i; 0 = gridDim.x
   ConvParams p[3];
 };
 

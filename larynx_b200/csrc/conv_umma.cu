@@ -1,39 +1,47 @@
 // conv_umma.cu — launcher of the tcgen05 implicit-GEMM conv (conv_umma.cuh).
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "conv_umma.cuh"
 #include "kernels.cuh"
 
 namespace b2 {
 
-template <int MT, int NSPLIT, int EW, int WST, int AST, int G>
+template <int MT, int NSPLIT, int EW, int WST, int AST, int G, int NBUF>
 static void set_attr_umma() {
-  B2_CUDA(cudaFuncSetAttribute(conv_umma_kernel<MT, NSPLIT, EW, WST, AST, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  B2_CUDA(cudaFuncSetAttribute(conv_umma_kernel<MT, NSPLIT, EW, WST, AST, G, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 }
 
-// kernel variants (MT, NSPLIT, EW, WST, AST, G)
-#define UMMA_BIG 1, 2, 8, 3, 2, 1        /* large grids: two CTAs per SM */
-#define UMMA_BIG2 2, 2, 8, 3, 2, 1       /* 256-row tiles, NT <= 64 (HiFi-GAN stage 3): half the weight traffic and per-CTA set-up, still two CTAs per SM */
-#define UMMA_TALL128 2, 2, 16, 8, 2, 1    /* experiment: 256-row tiles at NT = 128, whole SM (TMEM 512 columns), deep weight ring */
-#define UMMA_BIG4 4, 2, 8, 3, 1, 1       /* 512-row tiles, NT <= 32 and one input chunk (stage 4) */
-#define UMMA_SMALL128 1, 2, 16, 3, 2, 2  /* small grids, NT = 128: 2 taps (32 KB) per weight slot */
-#define UMMA_SMALL64 1, 2, 16, 3, 3, 5   /* small grids, NT <= 64: up to 5 taps (40 KB) per slot, 3 activation stages */
-#define UMMA_ENC128 1, 3, 16, 3, 2, 1    /* 3-way split (text encoder) */
-#define UMMA_ENC64 1, 3, 16, 3, 2, 3
+// kernel variants (MT, NSPLIT, EW, WST, AST, G, NBUF)
+#define UMMA_BIG 1, 2, 8, 3, 2, 1, 1        /* large grids: two CTAs per SM */
+#define UMMA_BIG2 2, 2, 8, 3, 2, 1, 1       /* 256-row tiles, NT <= 64 (HiFi-GAN stage 3): half the weight traffic and per-CTA set-up, still two CTAs per SM */
+#define UMMA_BIG4 4, 2, 8, 3, 1, 1, 1       /* 512-row tiles, NT <= 32 and one input chunk (stage 4) */
+#define UMMA_SMALL128 1, 2, 16, 3, 2, 2, 1  /* small grids, NT = 128: 2 taps (32 KB) per weight slot */
+#define UMMA_SMALL64 1, 2, 16, 3, 3, 5, 1   /* small grids, NT <= 64: up to 5 taps (40 KB) per slot, 3 activation stages */
+#define UMMA_ENC128 1, 3, 16, 3, 2, 1, 1    /* 3-way split (text encoder) */
+#define UMMA_ENC64 1, 3, 16, 3, 2, 3, 1
+/* persistent launches: one CTA per SM walks several time tiles; two accumulator buffers (all 512 TMEM columns), 16
+ * epilogue warps drain one buffer while the MMA warp fills the other; deep weight rings (the SM is not shared) */
+#define UMMA_P128 1, 2, 16, 9, 2, 1, 2      /* NT = 128: 9 x 16 KB weight slots */
+#define UMMA_P64 2, 2, 16, 6, 2, 2, 2       /* NT <= 64, 256-row tiles: 6 x 2 taps x 8 KB */
+#define UMMA_P32 4, 2, 16, 3, 2, 4, 2       /* NT <= 32, 512-row tiles, one input chunk: 3 x 4 taps x 4 KB */
 
 void conv_umma_init_attributes() {
   set_attr_umma<UMMA_BIG>();
   set_attr_umma<UMMA_BIG2>();
   set_attr_umma<UMMA_BIG4>();
-  set_attr_umma<UMMA_TALL128>();
+  set_attr_umma<UMMA_P128>();
+  set_attr_umma<UMMA_P64>();
+  set_attr_umma<UMMA_P32>();
   set_attr_umma<UMMA_SMALL128>();
   set_attr_umma<UMMA_SMALL64>();
   set_attr_umma<UMMA_ENC128>();
   set_attr_umma<UMMA_ENC64>();
 }
 
-template <int MT, int NSPLIT, int EW, int WST, int AST, int G>
-static void launch_umma_cfg(const ConvBatch& pb, int batch, int Lmax, cudaStream_t s) {
+template <int MT, int NSPLIT, int EW, int WST, int AST, int G, int NBUF>
+static void launch_umma_cfg(const ConvBatch& pb, int batch, int Lmax, cudaStream_t s, int grid_x = 0) {
   const ConvParams& p = pb.p[0];
   for (int i = 0; i < pb.n; ++i) {  // images are sized for whole tiles of this variant
     const ConvParams& q = pb.p[i];
@@ -44,10 +52,13 @@ static void launch_umma_cfg(const ConvBatch& pb, int batch, int Lmax, cudaStream
   const size_t smem = UmmaCfg<MT>::smem_bytes(NSPLIT, p.um_nt, WST, AST, G);
   B2_CHECK(smem <= 227 * 1024, "conv_umma: shared memory budget exceeded");
   const int ntiles = (p.Cout + p.um_nt - 1) / p.um_nt;
-  dim3 grid((Lmax + MT * 128 - 1) / (MT * 128), ntiles, batch * pb.n);
+  const int m_tiles = (Lmax + MT * 128 - 1) / (MT * 128);
+  B2_CHECK(NBUF * NSPLIT * MT * p.um_nt <= 512, "conv_umma: accumulators exceed the 512 TMEM columns");
+  B2_CHECK(NBUF == 2 || grid_x == 0, "conv_umma: single-buffer variants take one tile per CTA");
+  dim3 grid(grid_x > 0 ? std::min(grid_x, m_tiles) : m_tiles, ntiles, batch * pb.n);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
-  cfg.blockDim = dim3(EW * 32 + 64);
+  cfg.blockDim = dim3(EW * 32 + 64 + (NBUF == 2 ? 32 : 0));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
@@ -55,7 +66,7 @@ static void launch_umma_cfg(const ConvBatch& pb, int batch, int Lmax, cudaStream
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  B2_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<MT, NSPLIT, EW, WST, AST, G>, pb));
+  B2_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<MT, NSPLIT, EW, WST, AST, G, NBUF>, pb));
 }
 
 int launch_conv_umma_batch(const ConvParams* ps, int n, int batch, int Lmax, cudaStream_t stream) {
@@ -81,8 +92,47 @@ int launch_conv_umma_batch(const ConvParams* ps, int n, int batch, int Lmax, cud
   // tuning knobs (thread-safe one-time init).  Narrow layers with very many time tiles (HiFi-GAN stages 3 and 4) are
   // bound by per-CTA set-up and by re-streaming the weights for every 128 rows: taller tiles amortise both.
   static const long long mt_min = [] { const char* e = getenv("B200TTS_MT_MIN"); return e ? atoll(e) : 1184LL; }();
-  static const long long tall128_min = [] { const char* e = getenv("B200TTS_TALL128_MIN"); return e ? atoll(e) : (1LL << 40); }();
   static const long long ew16_max = [] { const char* e = getenv("B200TTS_EW16_MAX"); return e ? atoll(e) : 148LL; }();
+  // Persistent launch: one CTA per SM; the 148 CTAs are split between the convs (branches) of the launch in proportion
+  // to their cost per tile, max(mainloop ~ K * input chunks, epilogue), and each CTA walks the time tiles of its
+  // (n-tile, item, branch) with a stride of gx[branch].
+  static const int persist_min = [] { const char* e = getenv("B200TTS_PERSIST_MIN"); return e ? atoi(e) : 3; }();
+  static const int persist_ctas = [] { const char* e = getenv("B200TTS_PERSIST_CTAS"); return e ? atoi(e) : 148; }();
+  static const int epi_units = [] { const char* e = getenv("B200TTS_EPI_UNITS"); return e ? atoi(e) : 15; }();
+  const long long per = (long long)ntiles * batch;
+  if (p.um_nsplit == 2 && p.xp != nullptr && per * n <= persist_ctas) {
+    const int mt = p.um_nt <= 32 && p.Cin <= 32 ? 4 : (p.um_nt <= 64 ? 2 : 1);
+    const int m_tiles = (Lmax + mt * 128 - 1) / (mt * 128);
+    int a[3] = {1, 1, 1}, w[3];
+    for (int i = 0; i < n; ++i) w[i] = std::max(ps[i].K * ((ps[i].Cin + 31) / 32), epi_units);
+    long long total = per * n;
+    while (total + per <= persist_ctas) {
+      int worst = 0;
+      long long worst_cost = -1;
+      for (int i = 0; i < n; ++i) {
+        const long long cost = (long long)((m_tiles + a[i] - 1) / a[i]) * w[i];
+        if (cost > worst_cost) { worst_cost = cost; worst = i; }
+      }
+      if (a[worst] >= m_tiles) break;
+      a[worst]++;
+      total += per;
+    }
+    int min_tpc = 1 << 30, gmax = 0;
+    for (int i = 0; i < n; ++i) {
+      const int tpc = (m_tiles + a[i] - 1) / a[i];
+      pb.gx[i] = (m_tiles + tpc - 1) / tpc;
+      min_tpc = std::min(min_tpc, tpc);
+      gmax = std::max(gmax, pb.gx[i]);
+    }
+    if (min_tpc >= persist_min) {
+      if (mt == 4) launch_umma_cfg<UMMA_P32>(pb, batch, Lmax, stream, gmax);
+      else if (mt == 2) launch_umma_cfg<UMMA_P64>(pb, batch, Lmax, stream, gmax);
+      else launch_umma_cfg<UMMA_P128>(pb, batch, Lmax, stream, gmax);
+      B2_CUDA(cudaGetLastError());
+      return 1;
+    }
+    for (int i = 0; i < n; ++i) pb.gx[i] = 0;
+  }
   if (p.um_nsplit == 3) {
     if (p.um_nt <= 64) launch_umma_cfg<UMMA_ENC64>(pb, batch, Lmax, stream);
     else launch_umma_cfg<UMMA_ENC128>(pb, batch, Lmax, stream);
@@ -90,8 +140,6 @@ int launch_conv_umma_batch(const ConvParams* ps, int n, int batch, int Lmax, cud
     launch_umma_cfg<UMMA_BIG4>(pb, batch, Lmax, stream);
   } else if (ctas1 >= mt_min && p.um_nt <= 64) {
     launch_umma_cfg<UMMA_BIG2>(pb, batch, Lmax, stream);
-  } else if (ctas1 >= tall128_min && p.um_nt == 128) {
-    launch_umma_cfg<UMMA_TALL128>(pb, batch, Lmax, stream);
   } else if (ctas1 > ew16_max) {
     launch_umma_cfg<UMMA_BIG>(pb, batch, Lmax, stream);
   } else if (p.um_nt <= 64) {

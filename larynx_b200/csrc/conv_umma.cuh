@@ -163,16 +163,24 @@ __device__ __forceinline__ void plane_store4(const PlaneOut& po, int kc, int bof
 // where a CTA has the SM to itself and the serial latency of one tile is what matters.
 // AST: activation ring depth (per 32-channel chunk); G: conv taps per weight stage (one bulk copy, one wait, one
 // commit per stage — the single MMA-issuing warp is the serial resource of the main loop, so fewer, fatter stages).
-template <int MT, int NSPLIT, int EW, int WST, int AST, int G>
-__global__ void __launch_bounds__(EW * 32 + 64, EW == 8 ? 2 : 1) conv_umma_kernel(const __grid_constant__ ConvBatch pb) {
+// NBUF: accumulator buffers in TMEM.  A CTA walks the time tiles blockIdx.x, blockIdx.x + gridDim.x, ... of its
+// (n-tile, item/branch); with NBUF = 2 the MMA warp fills one buffer while the epilogue warps drain the other, and the
+// operand rings run ahead into the next tile, so the tensor pipe does not idle during epilogues ("persistent" launch:
+// gridDim.x < number of tiles).  With gridDim.x = number of tiles every CTA has one tile (the classic launch).
+template <int MT, int NSPLIT, int EW, int WST, int AST, int G, int NBUF>
+__global__ void __launch_bounds__(EW * 32 + 64 + (NBUF == 2 ? 32 : 0), EW == 8 ? 2 : 1)
+    conv_umma_kernel(const __grid_constant__ ConvBatch pb) {
   using namespace umma;
   const ConvParams& p = pb.p[blockIdx.z / pb.zb];
   using C = UmmaCfg<MT>;
   constexpr int RA = C::RA;
   constexpr int UM_WSTAGES = WST;
   constexpr int UM_NPROD = EW * 32;
-  constexpr int UM_NT_THREADS = UM_NPROD + 64;
-  constexpr int W_MMA = EW, W_LOAD = EW + 1;
+  // NBUF = 2 (several tiles per CTA): the activation bulk copies get a warp of their own so that they run ahead into the
+  // next tile; NBUF = 1 launches give every CTA exactly one tile and thread 0 issues them before it joins the epilogue
+  constexpr bool A_WARP = NBUF == 2;
+  constexpr int UM_NT_THREADS = UM_NPROD + 64 + (A_WARP ? 32 : 0);
+  constexpr int W_MMA = EW, W_LOAD = EW + 1, W_ALOAD = EW + 2;
   static_assert(WST <= UM_WSTAGES_MAX, "weight ring too deep");
   constexpr int NACC = NSPLIT;  // one fp32 accumulator per magnitude class of split products: the tensor core
                                 // truncates when it adds into the accumulator, so the long hi*hi chain must not
@@ -191,9 +199,11 @@ __global__ void __launch_bounds__(EW * 32 + 64, EW == 8 ? 2 : 1) conv_umma_kerne
   uint64_t* a_empty = bars + 4;   // [AST <= 4]
   uint64_t* w_full = bars + 8;    // [UM_WSTAGES]
   uint64_t* w_empty = bars + 24;  // [UM_WSTAGES]
-  uint64_t* acc_full = bars + 40; // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 41);
-  float* s_bias = reinterpret_cast<float*>(bars + 44);  // [NT] bias of this N tile
+  uint64_t* acc_full = bars + 40;   // [NBUF <= 2]  MMA -> epilogue
+  uint64_t* acc_empty = bars + 42;  // [NBUF <= 2]  epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 44);
+  float* s_bias = reinterpret_cast<float*>(bars + 46);  // [NT] bias of this N tile
+  static_assert(NBUF == 1 || NBUF == 2, "one or two accumulator buffers");
   static_assert(AST <= 4, "activation ring too deep");
   float* s_inv = s_bias + 256;                          // [16]      coupling: W^-1
   float* s_anb = s_inv + 16;                            // [2*half]  ActNorm bias
@@ -201,16 +211,18 @@ __global__ void __launch_bounds__(EW * 32 + 64, EW == 8 ? 2 : 1) conv_umma_kerne
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.z % pb.zb;
-  const int t0 = blockIdx.x * (MT * 128);
   const int ntile = blockIdx.y;
   const int n0 = ntile * NT;
   const int Lb = p.lens ? p.lens[b] * p.len_mul : p.Lin;
-  if (t0 >= Lb) return;
+  const int m_tiles = (Lb + MT * 128 - 1) / (MT * 128);
+  const int gstride = pb.gx[blockIdx.z / pb.zb] > 0 ? pb.gx[blockIdx.z / pb.zb] : (int)gridDim.x;  // CTAs sharing these tiles
+  if ((int)blockIdx.x >= m_tiles || (int)blockIdx.x >= gstride) return;
+  constexpr uint32_t ACC_COLS = NACC * MT;  // x NT: TMEM columns of one accumulator buffer
   const int K = p.K, dil = p.dil;
   const int nch = (p.Cin + UM_BKC - 1) / UM_BKC;
   const bool planes_in = p.xp != nullptr;
   uint32_t tmem_cols = 32;
-  while (tmem_cols < (uint32_t)(NACC * MT * NT)) tmem_cols <<= 1;
+  while (tmem_cols < (uint32_t)(NBUF * NACC * MT * NT)) tmem_cols <<= 1;
 
   if (tid == 0) UM_TRACE(0);
   if (tid == 0) {
@@ -222,7 +234,10 @@ __global__ void __launch_bounds__(EW * 32 + 64, EW == 8 ? 2 : 1) conv_umma_kerne
       mbar_init(&w_full[i], 1);
       mbar_init(&w_empty[i], 1);
     }
-    mbar_init(acc_full, 1);
+    for (int i = 0; i < NBUF; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], EW);  // one arrival per epilogue warp
+    }
     fence_barrier_init();
   }
   if (warp == W_MMA) tmem_alloc(tmem_slot, tmem_cols);
@@ -250,33 +265,73 @@ __global__ void __launch_bounds__(EW * 32 + 64, EW == 8 ? 2 : 1) conv_umma_kerne
       const unsigned char* gw = reinterpret_cast<const unsigned char*>(p.wu) + (size_t)ntile * nch * K * w_stage;
       int s = 0;
       uint32_t ph = 1;  // parity to wait for on w_empty (fresh barrier: passes)
-      for (int c = 0; c < nch; ++c)
-        for (int k0 = 0; k0 < K; k0 += G) {
-          const uint32_t bytes = (uint32_t)min(G, K - k0) * w_stage;  // taps of one chunk are contiguous in the image
-          mbar_wait(&w_empty[s], ph);
-          mbar_arrive_expect_tx(&w_full[s], bytes);
-          bulk_g2s(sW + (size_t)s * w_ring, gw + ((size_t)c * K + k0) * w_stage, bytes, &w_full[s]);
-          if (++s == UM_WSTAGES) { s = 0; ph ^= 1; }
+      for (int mtile = blockIdx.x; mtile < m_tiles; mtile += gstride)
+        for (int c = 0; c < nch; ++c)
+          for (int k0 = 0; k0 < K; k0 += G) {
+            const uint32_t bytes = (uint32_t)min(G, K - k0) * w_stage;  // taps of one chunk are contiguous in the image
+            mbar_wait(&w_empty[s], ph);
+            mbar_arrive_expect_tx(&w_full[s], bytes);
+            bulk_g2s(sW + (size_t)s * w_ring, gw + ((size_t)c * K + k0) * w_stage, bytes, &w_full[s]);
+            if (++s == UM_WSTAGES) { s = 0; ph ^= 1; }
+          }
+    }
+  } else if (A_WARP && warp == W_ALOAD) {
+    // ===================== A by bulk copy from the producer's plane image (persistent launches) =====================
+    if (lane == 0 && planes_in) {
+      asm volatile("griddepcontrol.wait;" ::: "memory");  // activations are written by the previous grid
+      const unsigned char* xp = reinterpret_cast<const unsigned char*>(p.xp) + (size_t)b * p.xp_bs;
+      // only the rows the taps can reach: MT*128 + (K-1)*dil of the RA rows a stage has room for
+      const uint32_t kc_bytes = (uint32_t)(MT * 128 + (K - 1) * dil) * 16;
+      int as = 0;
+      uint32_t aph = 1;
+      for (int mtile = blockIdx.x; mtile < m_tiles; mtile += gstride) {
+        const long long row0 = (long long)mtile * (MT * 128) - p.pad_left + UM_PADL;
+        for (int c = 0; c < nch; ++c, as = (as + 1 == AST ? 0 : as + 1), aph ^= (as == 0)) {
+          mbar_wait(&a_empty[as], aph);
+          mbar_arrive_expect_tx(&a_full[as], NSPLIT * UM_KCH * kc_bytes);
+          unsigned char* dst = sA + (size_t)as * a_stage;
+          for (int sp = 0; sp < NSPLIT; ++sp)
+#pragma unroll
+            for (int kc = 0; kc < UM_KCH; ++kc)
+              bulk_g2s(dst + sp * a_split_bytes + kc * RA * 16,
+                       xp + (((size_t)sp * p.xp_kc + c * UM_KCH + kc) * p.xp_rows + row0) * 16, kc_bytes, &a_full[as]);
         }
+        if (!A_WARP) break;  // thread 0 joins the epilogue of its (only) tile
+      }
     }
   } else if (warp == W_MMA) {
     // ===================== MMA issuer =====================
     {
       // The whole warp runs this loop with uniform control flow so the descriptor arithmetic lives in uniform
       // registers (UTCHMMA takes its operands from the uniform register file); only lane 0 issues.
-      const uint32_t idesc = make_idesc_bf16_f32(128, NT);
+      // The weight image keeps the split planes of a k-chunk as adjacent row blocks, so one MMA with N = j*NT multiplies
+      // an activation plane with j weight planes at once and lands in j adjacent accumulator classes:
+      //   A_hi x [B_hi | B_lo (| B_lo2)] -> [c0 | c1 (| c2)],   A_lo x [B_hi (| B_lo)] -> [c1 (| c2)],   A_lo2 x B_hi -> c2.
+      // Fewer, wider MMAs: every MMA re-reads its 128x16 A block from shared memory, which (not the tensor pipe) bounds
+      // narrow-N MMAs.
+      const uint32_t idesc1 = make_idesc_bf16_f32(128, NT), idesc2 = make_idesc_bf16_f32(128, 2 * NT);
+      const uint32_t idesc3 = make_idesc_bf16_f32(128, 3 * NT);
+      const bool wide3 = NSPLIT == 3 && 3 * NT <= 256;
       // Descriptors differ only in the 14-bit start-address field (bytes >> 4): build them once and add offsets.
       const uint64_t a_desc0 = make_smem_desc(smem_u32(sA), RA * 16, 128);
-      const uint64_t b_desc0 = make_smem_desc(smem_u32(sW), NT * 16, 128);
-      const uint32_t a_ks = (2 * RA * 16) >> 4, b_ks = (2 * NT * 16) >> 4;  // next K=16 step
-      const uint32_t a_sp = a_split_bytes >> 4, b_sp = w_split_bytes >> 4;  // next split plane
-      const uint32_t a_mt = (128 * 16) >> 4;                                // next 128-row tile
+      const uint64_t b_desc0 = make_smem_desc(smem_u32(sW), NSPLIT * NT * 16, 128);
+      const uint32_t a_ks = (2 * RA * 16) >> 4, b_ks = (2 * NSPLIT * NT * 16) >> 4;  // next K=16 step
+      const uint32_t a_sp = a_split_bytes >> 4, b_sp = (NT * 16) >> 4;               // next split plane
+      const uint32_t a_mt = (128 * 16) >> 4;                                          // next 128-row tile
       int ws = 0, as = 0;
       uint32_t wph = 0, aph = 0;
+      int it = 0;
+      for (int mtile = blockIdx.x; mtile < m_tiles; mtile += gstride, ++it) {
+      const int buf = NBUF == 2 ? (it & 1) : 0;
+      const uint32_t use = NBUF == 2 ? (uint32_t)(it >> 1) : (uint32_t)it;
+      mbar_wait(&acc_empty[buf], (use & 1) ^ 1);  // the epilogue has drained this buffer (fresh barrier: passes)
+      tc_fence_after();
+      const uint32_t tm = tmem + (uint32_t)buf * (ACC_COLS * NT);
+      if (lane == 0 && it < 8) UM_TRACE(16 + it * 4 + 0);
       for (int c = 0; c < nch; ++c) {
         mbar_wait(&a_full[as], aph);
         tc_fence_after();
-        if (c == 0 && lane == 0) UM_TRACE(3);
+        if (c == 0 && lane == 0 && it == 0) UM_TRACE(3);
         const uint64_t a_c = a_desc0 + ((as * a_stage) >> 4);
         for (int k0 = 0; k0 < K; k0 += G) {
           mbar_wait(&w_full[ws], wph);
@@ -294,15 +349,19 @@ __global__ void __launch_bounds__(EW * 32 + 64, EW == 8 ? 2 : 1) conv_umma_kerne
                 for (int mt = 0; mt < MT; ++mt) {
                   const uint64_t a0 = a_k + ks * a_ks + mt * a_mt, b0 = b_k + ks * b_ks;
                   const uint32_t acc0 = ks == 0 ? first : 1u;
-                  const uint32_t d0 = tmem + (0 * MT + mt) * NT, d1 = tmem + (1 * MT + mt) * NT;
-                  mma_bf16_ss(d0, a0, b0, idesc, acc0);                // hi*hi
-                  mma_bf16_ss(d1, a0, b0 + b_sp, idesc, acc0);         // hi*lo
-                  mma_bf16_ss(d1, a0 + a_sp, b0, idesc, 1u);           // lo*hi
-                  if (NSPLIT == 3) {
-                    const uint32_t d2 = tmem + (2 * MT + mt) * NT;
-                    mma_bf16_ss(d2, a0 + a_sp, b0 + b_sp, idesc, acc0);  // lo*lo
-                    mma_bf16_ss(d2, a0, b0 + 2 * b_sp, idesc, 1u);       // hi*lo2
-                    mma_bf16_ss(d2, a0 + 2 * a_sp, b0, idesc, 1u);       // lo2*hi
+                  const uint32_t d0 = tm + (uint32_t)(mt * NACC) * NT;  // classes of one M tile are adjacent columns
+                  if (NSPLIT == 2) {
+                    mma_bf16_ss(d0, a0, b0, idesc2, acc0);              // hi x [hi|lo] -> [c0|c1]
+                    mma_bf16_ss(d0 + NT, a0 + a_sp, b0, idesc1, 1u);    // lo x hi      -> c1
+                  } else if (wide3) {
+                    mma_bf16_ss(d0, a0, b0, idesc3, acc0);                  // hi  x [hi|lo|lo2] -> [c0|c1|c2]
+                    mma_bf16_ss(d0 + NT, a0 + a_sp, b0, idesc2, 1u);        // lo  x [hi|lo]     -> [c1|c2]
+                    mma_bf16_ss(d0 + 2 * NT, a0 + 2 * a_sp, b0, idesc1, 1u);  // lo2 x hi          -> c2
+                  } else {
+                    mma_bf16_ss(d0, a0, b0, idesc2, acc0);                       // hi  x [hi|lo] -> [c0|c1]
+                    mma_bf16_ss(d0 + 2 * NT, a0, b0 + 2 * b_sp, idesc1, acc0);   // hi  x lo2     -> c2
+                    mma_bf16_ss(d0 + NT, a0 + a_sp, b0, idesc2, 1u);             // lo  x [hi|lo] -> [c1|c2]
+                    mma_bf16_ss(d0 + 2 * NT, a0 + 2 * a_sp, b0, idesc1, 1u);     // lo2 x hi      -> c2
                   }
                 }
               }
@@ -316,21 +375,25 @@ __global__ void __launch_bounds__(EW * 32 + 64, EW == 8 ? 2 : 1) conv_umma_kerne
         __syncwarp();
         if (++as == AST) { as = 0; aph ^= 1; }
       }
-      if (elect_one()) mma_commit(acc_full);
-      if (lane == 0) UM_TRACE(4);
+      if (elect_one()) mma_commit(&acc_full[buf]);
+      __syncwarp();
+      if (lane == 0 && it < 8) UM_TRACE(16 + it * 4 + 1);
+      if (lane == 0 && it == 0) UM_TRACE(4);
+      }
     }
   } else {
     // everything below reads activations written by the previous grid (weights above are static)
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (planes_in) {
-      // ===================== A by bulk copy from the producer's plane image =====================
-      if (tid == 0) {
-        const unsigned char* xp = reinterpret_cast<const unsigned char*>(p.xp) + (size_t)b * p.xp_bs;
-        const long long row0 = (long long)t0 - p.pad_left + UM_PADL;
-        // only the rows the taps can reach: MT*128 + (K-1)*dil of the RA rows a stage has room for
-        const uint32_t kc_bytes = (uint32_t)(MT * 128 + (K - 1) * dil) * 16;
-        int as = 0;
-        uint32_t aph = 1;
+    if (!A_WARP && planes_in && tid == 0) {
+      // ===================== A by bulk copy from the producer's plane image (one tile per CTA) =====================
+      asm volatile("griddepcontrol.wait;" ::: "memory");  // activations are written by the previous grid
+      const unsigned char* xp = reinterpret_cast<const unsigned char*>(p.xp) + (size_t)b * p.xp_bs;
+      // only the rows the taps can reach: MT*128 + (K-1)*dil of the RA rows a stage has room for
+      const uint32_t kc_bytes = (uint32_t)(MT * 128 + (K - 1) * dil) * 16;
+      int as = 0;
+      uint32_t aph = 1;
+      for (int mtile = blockIdx.x; mtile < m_tiles; mtile += gstride) {
+        const long long row0 = (long long)mtile * (MT * 128) - p.pad_left + UM_PADL;
         for (int c = 0; c < nch; ++c, as = (as + 1 == AST ? 0 : as + 1), aph ^= (as == 0)) {
           mbar_wait(&a_empty[as], aph);
           mbar_arrive_expect_tx(&a_full[as], NSPLIT * UM_KCH * kc_bytes);
@@ -340,19 +403,22 @@ __global__ void __launch_bounds__(EW * 32 + 64, EW == 8 ? 2 : 1) conv_umma_kerne
             for (int kc = 0; kc < UM_KCH; ++kc)
               bulk_g2s(dst + sp * a_split_bytes + kc * RA * 16,
                        xp + (((size_t)sp * p.xp_kc + c * UM_KCH + kc) * p.xp_rows + row0) * 16, kc_bytes, &a_full[as]);
-          if (c == 0) UM_TRACE(2);
-          if (c == nch - 1) UM_TRACE(5);
         }
+        if (!A_WARP) break;  // thread 0 joins the epilogue of its (only) tile
       }
-    } else {
+    }
+    int as = 0;        // gather-mode producer state of the activation ring (runs on across tiles)
+    uint32_t aph = 1;
+    int it = 0;
+    for (int mtile = blockIdx.x; mtile < m_tiles; mtile += gstride, ++it) {
+    const int t0 = mtile * (MT * 128);
+    if (!planes_in) {
       // ===================== A by gather + split (warps 0..7) =====================
       const float* xb = p.x + (size_t)b * p.x_bs;
       const float* xb2 = p.x2 ? p.x2 + (size_t)b * p.x_bs : nullptr;
       const float* xb3 = p.x3 ? p.x3 + (size_t)b * p.x_bs : nullptr;
       const int rows_used = MT * 128 + (K - 1) * dil;
       const bool three = xb2 != nullptr && xb3 != nullptr;  // MRF mean of three inputs (uniform)
-      int as = 0;
-      uint32_t aph = 1;
       for (int c = 0; c < nch; ++c, as = (as + 1 == AST ? 0 : as + 1), aph ^= (as == 0)) {
         mbar_wait(&a_empty[as], aph);
         unsigned char* dst = sA + (size_t)as * a_stage;
@@ -412,15 +478,19 @@ __global__ void __launch_bounds__(EW * 32 + 64, EW == 8 ? 2 : 1) conv_umma_kerne
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&a_full[as]);
-        if (tid == 0 && c == 0) UM_TRACE(2);
-        if (tid == 0 && c == nch - 1) UM_TRACE(5);
+        if (tid == 0 && c == 0 && it == 0) UM_TRACE(2);
+        if (tid == 0 && c == nch - 1 && it == 0) UM_TRACE(5);
       }
     }
 
-    // ===================== epilogue (warps 0..7) =====================
-    mbar_wait(acc_full, 0);
+    // ===================== epilogue (warps 0..EW-1) =====================
+    const int buf = NBUF == 2 ? (it & 1) : 0;
+    const uint32_t use = NBUF == 2 ? (uint32_t)(it >> 1) : (uint32_t)it;
+    mbar_wait(&acc_full[buf], use & 1);
     tc_fence_after();
-    if (tid == 0) UM_TRACE(6);
+    const uint32_t tm = tmem + (uint32_t)buf * (ACC_COLS * NT);
+    if (tid == 0 && it == 0) UM_TRACE(6);
+    if (tid == 0 && it < 8) UM_TRACE(16 + it * 4 + 2);
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
     const int wset = warp >> 2; // EW/4 warp sets share the (M tile, 32-column group) tasks round robin
     constexpr int NWS = EW / 4;
@@ -438,7 +508,7 @@ __global__ void __launch_bounds__(EW * 32 + 64, EW == 8 ? 2 : 1) conv_umma_kerne
       const int g = MT == 1 ? task : task / MT;
       const int t = t0 + mt * 128 + m;
       const bool t_ok = t < Lb;
-      po.pad_front = blockIdx.x == 0;
+      po.pad_front = mtile == 0;
       po.pad_tail = (long long)(t0 + MT * 128) >= Lb;
       po.m = mt * 128 + m;
       po2 = po;
@@ -446,14 +516,14 @@ __global__ void __launch_bounds__(EW * 32 + 64, EW == 8 ? 2 : 1) conv_umma_kerne
       float acc[32];
       {
         uint32_t raw[32];
-        const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * 32);
-        tmem_ld32(lane_addr + (uint32_t)(((NACC - 1) * MT + mt) * NT), raw);  // smallest magnitude class first
+        const uint32_t lane_addr = tm + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * 32);
+        tmem_ld32(lane_addr + (uint32_t)((mt * NACC + NACC - 1) * NT), raw);  // smallest magnitude class first
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(raw[j]);
 #pragma unroll
         for (int a = NACC - 2; a >= 0; --a) {
-          tmem_ld32(lane_addr + (uint32_t)((a * MT + mt) * NT), raw);
+          tmem_ld32(lane_addr + (uint32_t)((mt * NACC + a) * NT), raw);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(raw[j]);
@@ -462,7 +532,7 @@ __global__ void __launch_bounds__(EW * 32 + 64, EW == 8 ? 2 : 1) conv_umma_kerne
       const int nb = n0 + g * 32;  // packed channel of acc[0]
       const int jmax = min(32, min(NT - g * 32, p.Cout - nb));
       if (jmax <= 0) continue;
-      if (tid == 0 && task == wset) UM_TRACE(9);
+      if (tid == 0 && task == wset && it == 0) UM_TRACE(9);
       if (p.epi == EPI_PLAIN && u == 1) {
         float* __restrict__ yb = p.y + (size_t)b * p.y_bs + t;
         float rv[32];
@@ -624,13 +694,13 @@ __global__ void __launch_bounds__(EW * 32 + 64, EW == 8 ? 2 : 1) conv_umma_kerne
         }
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc[j] = (t_ok && j < jmax) ? old[j] + (acc[j] + s_bias[g * 32 + j]) : 0.f;
-        if (tid == 0 && task == wset) UM_TRACE(10);
+        if (tid == 0 && task == wset && it == 0) UM_TRACE(10);
         if (t_ok) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (j < jmax) db[(size_t)j * ld] = acc[j];
         }
-        if (tid == 0 && task == wset) UM_TRACE(11);
+        if (tid == 0 && task == wset && it == 0) UM_TRACE(11);
         const PlaneOut& pp = in_y ? po : po2;
         if (pp.base) {
           const int c0 = in_y ? nb : nb - p.split;
@@ -703,6 +773,12 @@ __global__ void __launch_bounds__(EW * 32 + 64, EW == 8 ? 2 : 1) conv_umma_kerne
             }
         }
       }
+    }
+    // this warp is done reading the accumulator buffer: hand it back to the MMA warp
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    if (tid == 0 && it < 8) UM_TRACE(16 + it * 4 + 3);
     }
   }
   if (tid == 0) UM_TRACE(7);

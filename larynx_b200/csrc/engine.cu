@@ -319,9 +319,9 @@ static void conv(b200tts_call* c, ConvParams& p, const ConvW& w, int batch, int 
     if (conv_trace()) {  // debug only (single-threaded use): per-phase timestamps of CTA (0,0,0), one line per conv
       static unsigned long long* dbg = nullptr;
       static unsigned long long last_end = 0;
-      if (!dbg) B2_CUDA(cudaMallocManaged(&dbg, 16 * sizeof(unsigned long long)));
+      if (!dbg) B2_CUDA(cudaMallocManaged(&dbg, 64 * sizeof(unsigned long long)));
       B2_CUDA(cudaDeviceSynchronize());
-      memset(dbg, 0, 16 * sizeof(unsigned long long));
+      memset(dbg, 0, 64 * sizeof(unsigned long long));
       p.dbg = dbg;
       c->launches += launch_conv_umma(p, batch, Lmax, s);
       B2_CUDA(cudaDeviceSynchronize());
@@ -330,6 +330,13 @@ static void conv(b200tts_call* c, ConvParams& p, const ConvW& w, int batch, int 
               (dbg[3] - dbg[1]) * 1e-3, (dbg[4] - dbg[1]) * 1e-3, (dbg[5] - dbg[1]) * 1e-3, (dbg[6] - dbg[1]) * 1e-3, (dbg[7] - dbg[6]) * 1e-3,
               (dbg[8] - dbg[7]) * 1e-3, (dbg[8] - dbg[0]) * 1e-3, dbg[9] ? (dbg[9] - dbg[6]) * 1e-3 : 0.0,
               dbg[10] ? (dbg[10] - dbg[9]) * 1e-3 : 0.0, dbg[11] ? (dbg[11] - dbg[10]) * 1e-3 : 0.0);
+      if (dbg[16]) {  // several tiles per CTA: per tile  mainloop start..end | epilogue start..end  (us since CTA start)
+        fprintf(stderr, "        tiles:");
+        for (int i = 0; i < 8 && dbg[16 + 4 * i]; ++i)
+          fprintf(stderr, "  [mma %.1f-%.1f epi %.1f-%.1f]", (dbg[16 + 4 * i] - dbg[0]) * 1e-3, (dbg[17 + 4 * i] - dbg[0]) * 1e-3,
+                  (dbg[18 + 4 * i] - dbg[0]) * 1e-3, (dbg[19 + 4 * i] - dbg[0]) * 1e-3);
+        fprintf(stderr, "\n");
+      }
       last_end = dbg[8];
       return;
     }

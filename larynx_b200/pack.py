@@ -102,9 +102,10 @@ UMMA_BKC = 32  # input channels per pipeline stage (csrc/conv_umma.cuh: UM_BKC)
 
 def umma_image(w: np.ndarray, nsplit: int, nt_max: int = 128):
     """[Cout][Cin][K] fp32 -> bf16 split image for conv_umma_kernel:
-    [n-tile][ci-chunk of 32][tap][split plane hi/lo(/lo2)][k-chunk of 8 (4)][NT rows][8] uint16.
+    [n-tile][ci-chunk of 32][tap][k-chunk of 8 (4)][split plane hi/lo(/lo2)][NT rows][8] uint16.
     Each (n-tile, ci-chunk, tap) block is one contiguous cp.async.bulk transfer and already has the
-    K-major SWIZZLE_NONE UMMA operand layout (rows 16 B apart)."""
+    K-major SWIZZLE_NONE UMMA operand layout (rows 16 B apart).  The split planes of one k-chunk are adjacent
+    row blocks, so ONE MMA with N = 2*NT (3*NT) multiplies an activation plane with hi|lo(|lo2) at once."""
     cout, cin, k = w.shape
     nt = pick_nt(cout, nt_max)
     ntiles = (cout + nt - 1) // nt
@@ -119,7 +120,7 @@ def umma_image(w: np.ndarray, nsplit: int, nt_max: int = 128):
         rem = (rem - from_bf16_bits(bits)).astype(np.float32)
     img = np.stack(planes, 0)  # [split][N][C][K]
     img = img.reshape(nsplit, ntiles, nt, nch, UMMA_BKC // 8, 8, k)
-    img = np.transpose(img, (1, 3, 6, 0, 4, 2, 5))  # [ntile][nch][K][split][kc][NT][8]
+    img = np.transpose(img, (1, 3, 6, 4, 0, 2, 5))  # [ntile][nch][K][kc][split][NT][8]
     meta = np.array([nt, nsplit, nch, k, ntiles, cout, cin, 0], dtype=np.float32)
     return np.ascontiguousarray(img).reshape(-1), meta
 

@@ -124,7 +124,7 @@ def test_fails_loudly_without_device_or_with_bad_blob():
 
 
 def test_bf16_split_images_reconstruct_weights():
-    """umma_image: [n-tile][ci-chunk][tap][plane][4][NT][8]; hi + lo (+ lo2) must reconstruct the fp32 weights."""
+    """umma_image: [n-tile][ci-chunk][tap][4][plane][NT][8]; hi + lo (+ lo2) must reconstruct the fp32 weights."""
     rs = np.random.RandomState(2)
     for cout, cin, k, nsplit, nt_max in ((160, 192, 1, 2, 64), (384, 192, 5, 2, 128), (80, 192, 1, 3, 64), (64, 64, 11, 2, 128)):
         w = rs.standard_normal((cout, cin, k)).astype(np.float32)
@@ -132,13 +132,13 @@ def test_bf16_split_images_reconstruct_weights():
         nt, ns, nch, kk, ntiles = (int(meta[i]) for i in range(5))
         assert nt == pack.pick_nt(cout, nt_max) and ns == nsplit and kk == k and nch == (cin + 31) // 32
         assert nt % 16 == 0 and nt <= nt_max and ntiles * nt >= cout
-        planes = pack.from_bf16_bits(img.reshape(ntiles, nch, k, nsplit, 4, nt, 8))
-        rec = planes.sum(axis=3)  # [ntile][nch][k][4][nt][8]
+        planes = pack.from_bf16_bits(img.reshape(ntiles, nch, k, 4, nsplit, nt, 8))
+        rec = planes.sum(axis=4)  # [ntile][nch][k][4][nt][8]
         rec = np.transpose(rec, (0, 4, 1, 3, 5, 2)).reshape(ntiles * nt, nch * 32, k)[:cout, :cin]
         tol = 2.0 ** (-16 if nsplit == 2 else -23) * np.abs(w).max()
         assert np.abs(rec - w).max() <= tol
         # padding (channels beyond Cout / Cin) is exactly zero, so garbage x 0 never reaches an accumulator
-        full = np.transpose(planes.sum(axis=3), (0, 4, 1, 3, 5, 2)).reshape(ntiles * nt, nch * 32, k)
+        full = np.transpose(planes.sum(axis=4), (0, 4, 1, 3, 5, 2)).reshape(ntiles * nt, nch * 32, k)
         assert np.all(full[cout:] == 0) and np.all(full[:, cin:] == 0)
 
 

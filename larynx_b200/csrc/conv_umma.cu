@@ -91,7 +91,7 @@ int launch_conv_umma_batch(const ConvParams* ps, int n, int batch, int Lmax, cud
   const long long ctas1 = (long long)((Lmax + 127) / 128) * ntiles * batch * n;
   // tuning knobs (thread-safe one-time init).  Narrow layers with very many time tiles (HiFi-GAN stages 3 and 4) are
   // bound by per-CTA set-up and by re-streaming the weights for every 128 rows: taller tiles amortise both.
-  static const long long mt_min = [] { const char* e = getenv("B200TTS_MT_MIN"); return e ? atoll(e) : 1184LL; }();
+  static const long long mt_min = [] { const char* e = getenv("B200TTS_MT_MIN"); return e ? atoll(e) : 149LL; }();
   static const long long ew16_max = [] { const char* e = getenv("B200TTS_EW16_MAX"); return e ? atoll(e) : 148LL; }();
   // Persistent launch: one CTA per SM; the 148 CTAs are split between the convs (branches) of the launch in proportion
   // to their cost per tile, max(mainloop ~ K * input chunks, epilogue), and each CTA walks the time tiles of its

@@ -350,12 +350,13 @@ def bench_ours(args, rank, world, local_rank):
             "gpu_launches_per_step": int(launches // K),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": voc_tflops, "peak": tensor_peak, "unit": "TFLOP/s",
-                         "frac": voc_tflops / tensor_peak, "traffic": 2.4e7,
-                         "traffic_note": "dram__bytes_read+write of one stage-1 ResBlock launch (3 MRF branches, C=256, L=4016) from the ncu --set full "
-                                         "capture in profiles/r1f_ncu_full_conv_umma_stage1.csv: 18-31 MB (cold weights), activations stay in L2",
+                         "frac": voc_tflops / tensor_peak, "traffic": 6.1e7,
+                         "traffic_note": "dram__bytes_read+write of one stage-2 ResBlock launch (3 MRF branches, C=128, L=32128; the largest share of the "
+                                         "vocoder) from the ncu --set full capture in profiles/r1h_ncu_full_stage2_resblock.csv: 61 MB (112 MB on the first, "
+                                         "cold pass) against 49 MB of activation images it reads + 49 MB it writes: they largely stay in the 126 MB L2",
                          "peak_source": peak_src + " bf16 dense (burst)",
-                         "kernel": f"conv_umma_kernel<MT,NSPLIT,EW,WST> (tcgen05 kind::f16, bf16x3 split = 3 MMAs per algorithmic MAC-tile, fp32 TMEM "
-                                   f"accumulators): HiFi-GAN pass ({voc_launches} launches, {vms:.3f} ms, {HIFIGAN_MFLOP_PER_FRAME:.1f} MFLOP/frame x {frames} frames)",
+                         "kernel": f"conv_umma_kernel<MT,NSPLIT,EW,WST,AST,G,NBUF> (tcgen05 kind::f16, bf16 hi/lo split = 3 products per algorithmic MAC "
+                                   f"issued as 2 wide-N MMAs, fp32 TMEM accumulators, persistent double-buffered launches for the long stages): HiFi-GAN pass ({voc_launches} launches, {vms:.3f} ms, {HIFIGAN_MFLOP_PER_FRAME:.1f} MFLOP/frame x {frames} frames)",
                          "tensor_flops_issued_tflops": 3 * voc_tflops, "frac_tensor_issued": 3 * voc_tflops / tensor_peak,
                          "fp32_simt_peak_tflops": FP32_SIMT_PEAK_TFLOPS, "frac_of_fp32_simt_peak": voc_tflops / FP32_SIMT_PEAK_TFLOPS,
                          "step_tflops": step_flops / (ms_per_step * 1e-3) / 1e12,

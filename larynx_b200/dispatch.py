@@ -30,6 +30,26 @@ def shard_by_cost(costs: Sequence[float], world: int) -> List[List[int]]:
     return [sorted(x) for x in out]
 
 
+def bucket_by_length(lengths: Sequence[int], batch: int, max_cost: Optional[int] = None) -> List[List[int]]:
+    """Micro-batches of similar length for the fused batch path: sentences sorted by phoneme count
+    (stable), cut into runs of at most `batch` items and — if `max_cost` is given — at most `max_cost` phonemes of the
+    longest item times the item count (bounds the padded work and the workspace of a micro-batch).  Every index appears
+    exactly once; results are put back in submission order by the caller, like the reference yields its futures in
+    submission order (larynx/__init__.py:187-190)."""
+    order = sorted(range(len(lengths)), key=lambda i: (int(lengths[i]), i))
+    out: List[List[int]] = []
+    cur: List[int] = []
+    for i in order:
+        longest = int(lengths[i])  # ascending order: the newcomer is the longest of the run
+        if cur and (len(cur) >= batch or (max_cost is not None and longest * (len(cur) + 1) > max_cost)):
+            out.append(cur)
+            cur = []
+        cur.append(i)
+    if cur:
+        out.append(cur)
+    return out
+
+
 def broadcast_blob(make_blob: Optional[Callable[[], np.ndarray]], device=None, src: int = 0):
     """Rank `src` calls make_blob() (a uint8 numpy array); everyone returns the same bytes as a torch
     uint8 tensor on `device` (cuda:<local_rank> with NCCL, cpu with gloo).  Single-process: no collective."""

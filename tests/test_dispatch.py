@@ -63,3 +63,19 @@ def test_broadcast_and_gather_world2():
     assert all(p.exitcode == 0 for p in procs)
     got = sorted(q.get(timeout=5) for _ in range(2))
     assert got == [(0, "ok"), (1, "ok")]
+
+
+def test_bucket_by_length_covers_every_sentence_once():
+    rs = np.random.RandomState(0)
+    lens = rs.randint(1, 300, 97)
+    for batch, cap in ((8, None), (16, 2000), (1, None)):
+        buckets = dispatch.bucket_by_length(lens, batch, cap)
+        flat = sorted(i for b in buckets for i in b)
+        assert flat == list(range(97))
+        assert all(1 <= len(b) <= batch for b in buckets)
+        if cap is not None:
+            assert all(len(b) == 1 or max(lens[i] for i in b) * len(b) <= cap for b in buckets)
+        # similar lengths end up together: within a bucket the spread is small compared with the whole set
+        if batch > 1:
+            spread = np.mean([max(lens[i] for i in b) - min(lens[i] for i in b) for b in buckets])
+            assert spread < (lens.max() - lens.min()) / 4

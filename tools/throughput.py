@@ -18,12 +18,16 @@ import time
 import numpy as np
 
 sys.path.insert(0, ".")
-from larynx_b200 import host, synth  # noqa: E402
+from larynx_b200 import dispatch, host, synth  # noqa: E402
 from tests import common  # noqa: E402
 
 
-def run(glow, voc, glue, rows, n_threads: int, batch: int, denoise: float):
-    chunks = [rows[i : i + batch] for i in range(0, len(rows), batch)]
+def run(glow, voc, glue, rows, n_threads: int, batch: int, denoise: float, bucket: bool = False):
+    if bucket:  # length-bucketed micro-batches, longest first (larynx_b200.dispatch.bucket_by_length)
+        groups = dispatch.bucket_by_length([len(r) for r in rows], batch)[::-1]
+        chunks = [[rows[i] for i in g] for g in groups]
+    else:
+        chunks = [rows[i : i + batch] for i in range(0, len(rows), batch)]
     nxt = [0]
     lock = threading.Lock()
     frames = [0] * n_threads
@@ -61,6 +65,7 @@ def main():
     ap.add_argument("--threads", default="1,2,4,8")
     ap.add_argument("--batch", default="1,4,16,32")
     ap.add_argument("--denoise", type=float, default=0.0)
+    ap.add_argument("--bucket", action="store_true", help="sort sentences into micro-batches of similar length")
     a = ap.parse_args()
     glow, voc = common.product_glow(), common.product_hifi()
     glue = host.MelGlue.from_config(common.glow_cfg()["audio"])
@@ -75,9 +80,9 @@ def main():
         for t in (int(x) for x in a.threads.split(",")):
             if b * t > 64:  # every call context owns its workspaces (~0.5 GB per batched 6 s sentence): bound the footprint
                 continue
-            run(glow, voc, glue, rows[: max(2 * b * t, 8)], t, b, a.denoise)  # warm-up: arenas, attributes
-            dt, fr = run(glow, voc, glue, rows, t, b, a.denoise)
-            print(json.dumps({"threads": t, "batch": b, "ids": a.ids, "denoise": a.denoise, "sentences": a.n, "wall_s": round(dt, 4),
+            run(glow, voc, glue, rows[: max(2 * b * t, 8)], t, b, a.denoise, a.bucket)  # warm-up: arenas, attributes
+            dt, fr = run(glow, voc, glue, rows, t, b, a.denoise, a.bucket)
+            print(json.dumps({"threads": t, "batch": b, "ids": a.ids, "denoise": a.denoise, "bucket": a.bucket, "sentences": a.n, "wall_s": round(dt, 4),
                               "utt_per_s": round(a.n / dt, 1), "mel_frames_per_s": round(fr / dt, 1),
                               "x_realtime": round(fr * 256 / 22050 / dt, 1)}), flush=True)
 

@@ -151,6 +151,48 @@ int launch_conv_umma_batch(const ConvParams* ps, int n, int batch, int Lmax, cud
   return 1;
 }
 
+// Operand image of leaky_relu(((x1 + x2) + x3) / div, slope): the MRF mean that feeds the next upsampler
+// (hifi_gan/models.py:191-197 followed by :189), written ONCE instead of being re-gathered by every n-tile CTA of the
+// upsampler conv.  Covers every row of the image: zero rows in front (UM_PADL), behind each item's length and in the tail.
+// Same expression order as the gather path of conv_umma_kernel, so both paths produce identical bits.
+__global__ void __launch_bounds__(256) mean3_image_kernel(const float* __restrict__ x1, const float* __restrict__ x2,
+                                                          const float* __restrict__ x3, long long bs, int ld, float div,
+                                                          float slope, const int* __restrict__ lens, int len_mul,
+                                                          unsigned char* __restrict__ img, long long img_bs, int kc_total,
+                                                          int rows) {
+  const int b = blockIdx.z, kc = blockIdx.y;
+  const int r = blockIdx.x * 256 + threadIdx.x;
+  if (r >= rows) return;
+  const int t = r - UM_PADL;
+  const bool ok = t >= 0 && t < lens[b] * len_mul;
+  float v[8];
+  const size_t base = (size_t)b * bs + (size_t)(kc * 8) * ld + (ok ? t : 0);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const size_t off = base + (size_t)e * ld;
+    float a = (x1[off] + x2[off]) + x3[off];
+    a = a / div;
+    a = a > 0.f ? a : a * slope;
+    v[e] = ok ? a : 0.f;
+  }
+  uint4 q[2];
+  split8<2>(v, q);
+  unsigned char* o = img + (size_t)b * img_bs + ((size_t)kc * rows + r) * 16;
+  *reinterpret_cast<uint4*>(o) = q[0];
+  *reinterpret_cast<uint4*>(o + (size_t)kc_total * rows * 16) = q[1];
+}
+
+void launch_mean3_image(const float* x1, const float* x2, const float* x3, long long bs, int ld, int C, float div, float slope,
+                        const int* lens, int len_mul, int batch, void* img, long long img_bs, int kc_total, int rows,
+                        cudaStream_t s) {
+  B2_CHECK(C % 8 == 0 && C / 8 <= kc_total, "mean image: channel count does not fit the image");
+  if (batch <= 0 || rows <= 0) return;
+  dim3 grid((rows + 255) / 256, C / 8, batch);
+  mean3_image_kernel<<<grid, 256, 0, s>>>(x1, x2, x3, bs, ld, div, slope, lens, len_mul, reinterpret_cast<unsigned char*>(img),
+                                          img_bs, kc_total, rows);
+  B2_CUDA(cudaGetLastError());
+}
+
 int launch_conv_umma(const ConvParams& p, int batch, int Lmax, cudaStream_t stream) {
   return launch_conv_umma_batch(&p, 1, batch, Lmax, stream);
 }

@@ -301,6 +301,10 @@ static bool res_from_planes() {
   static const bool on = getenv("B200TTS_RES_FP32") == nullptr;
   return on;
 }
+static bool mean_image() {
+  static const bool on = getenv("B200TTS_NO_MEAN_IMAGE") == nullptr;
+  return on;
+}
 static bool conv_trace() {
   static const bool on = getenv("B200TTS_CONV_TRACE") != nullptr;
   return on;
@@ -828,6 +832,8 @@ static void hifigan_run(const b200tts_hifigan* m, b200tts_call* c, const float* 
     const float *in1 = P, *in2 = nullptr, *in3 = nullptr;
     float in_div = 1.f;
     int Lin_ld = ld0, len_mul = 1, cin = m->C0;
+    Planes prev_U_p;
+    bool prev_ump = false;
     for (int i = 0; i < m->n_ups; ++i) {
       const int u = m->up_rate[i], cout = m->C0 >> (i + 1);
       const int Lld = Lin_ld * u;
@@ -864,7 +870,16 @@ static void hifigan_run(const b200tts_hifigan* m, b200tts_call* c, const float* 
         p.lens = frames_d; p.len_mul = len_mul; p.Lin = Tmax * len_mul;
         if (m->ups_ps[i].wu && use_umma()) {
           p.pix = u; p.pad_left = 1;  // one 3-tap conv, cout*u pixel-shuffled channels
-          if (um && i == 0) set_in(p, P_p);  // later stages read the MRF mean of three tensors (fp32 gather)
+          if (um && i == 0) {
+            set_in(p, P_p);
+          } else if (um && prev_ump && in2 && in3 && mean_image()) {
+            // later stages read the MRF mean of three tensors: build its operand image once (into the previous stage's
+            // dead U image) instead of letting each of the upsampler's n-tile CTAs gather and split it again
+            launch_mean3_image(in1, in2, in3, (long long)cin * Lin_ld, Lin_ld, cin, in_div, 0.1f, frames_d, len_mul, batch,
+                               prev_U_p.ptr, prev_U_p.bs, prev_U_p.kc, prev_U_p.rows, s);
+            c->launches++;
+            set_in(p, prev_U_p);
+          }
           if (ump) set_out(p, U_p, 0.1f);
           conv(c, p, m->ups_ps[i], batch, Tmax * len_mul, s);
         } else {
@@ -995,6 +1010,8 @@ static void hifigan_run(const b200tts_hifigan* m, b200tts_call* c, const float* 
       }
       // the resblock result buffer: ResBlock1 -> R; ResBlock2 with ndil=2 -> last dst = R (d=1)
       in1 = bs_[1]; in2 = bs_[2]; in3 = bs_[3];
+      prev_U_p = U_p;
+      prev_ump = ump && m->n_kernels == 3;
       in_div = (float)m->n_kernels;
       Lin_ld = Lld;
       cin = cout;

@@ -56,4 +56,9 @@ void launch_stft_denoise(const float* pcm, int pcm_ld, const int* frames, int le
 void launch_overlap_add(const float* fr, long long fr_bs, const int* frames, int len_mul, int batch, int max_len,
                         float* pcm, int pcm_ld, unsigned int* peak_bits, cudaStream_t s);
 
+// bf16 hi/lo operand image of leaky_relu(((x1 + x2) + x3) / div, slope) for the tensor-core convs (conv_umma.cu)
+void launch_mean3_image(const float* x1, const float* x2, const float* x3, long long bs, int ld, int C, float div, float slope,
+                        const int* lens, int len_mul, int batch, void* img, long long img_bs, int kc_total, int rows,
+                        cudaStream_t s);
+
 }  // namespace b2

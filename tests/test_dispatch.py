@@ -79,3 +79,34 @@ def test_bucket_by_length_covers_every_sentence_once():
         if batch > 1:
             spread = np.mean([max(lens[i] for i in b) - min(lens[i] for i in b) for b in buckets])
             assert spread < (lens.max() - lens.min()) / 4
+
+
+def test_batch_scheduler_orders_results_and_propagates_errors():
+    from larynx_b200.scheduler import BatchScheduler
+
+    rs = np.random.RandomState(1)
+    rows = [rs.randint(1, 46, n) for n in rs.randint(0, 120, 41)]
+    rows[7] = np.zeros(0, dtype=np.int64)
+    calls = []
+
+    def fake(batch_rows, seed):
+        calls.append([len(r) for r in batch_rows])
+        return [np.full(len(r) * 3, len(r), dtype=np.int16) for r in batch_rows]
+
+    sch = BatchScheduler(max_batch=8, max_cost=400, workers=3, synth=fake)
+    out = sch.synthesize(rows)
+    assert [a.shape[0] for a in out] == [3 * len(r) for r in rows]
+    assert all(len(c) <= 8 and max(c) * len(c) <= 400 or len(c) == 1 for c in calls)
+    assert sorted(n for c in calls for n in c) == sorted(len(r) for r in rows if len(r))  # empty sentences never reach the device
+    seen = [i for i, _ in sch.stream(rows)]
+    assert seen == list(range(len(rows)))
+
+    def broken(batch_rows, seed):
+        raise ValueError("boom")
+
+    import pytest
+
+    with pytest.raises(ValueError):
+        BatchScheduler(max_batch=4, workers=2, synth=broken).synthesize(rows)
+    with pytest.raises(ValueError):
+        list(BatchScheduler(max_batch=4, workers=2, synth=broken).stream(rows))

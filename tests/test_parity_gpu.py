@@ -363,3 +363,26 @@ def test_device_resident_buffers():
     glow.model.decode(call, mel_d, ty, 0.667, eps_d, ty, 0)
     torch.cuda.synchronize()
     assert np.array_equal(mel_d.cpu().numpy(), mel_h)
+
+
+def test_batch_scheduler_matches_per_sentence_results():
+    """Length-bucketed micro-batches on two host threads return, in submission order, what each sentence gives alone."""
+    from larynx_b200.scheduler import BatchScheduler
+
+    glow, voc = common.product_glow(), common.product_hifi()
+    glue = host.MelGlue.from_config(common.glow_cfg()["audio"])
+    rs = np.random.RandomState(9)
+    rows = [synth.bench_ids(int(n), seed=500 + i) for i, n in enumerate(rs.randint(0, 60, 13))]
+    sch = BatchScheduler(glow, voc, glue, max_batch=4, max_cost=200, workers=2, noise_scale=0.0)
+    out = sch.synthesize(rows)
+    streamed = dict(sch.stream(rows))
+    assert len(out) == len(rows) and sorted(streamed) == list(range(len(rows)))
+    for i, r in enumerate(rows):
+        if len(r) == 0:
+            assert out[i].shape == (0,)
+            continue
+        one = host.synthesize_batch(glow, voc, glue, [r], noise_scale=0.0, want_float=True)
+        assert out[i].dtype == np.int16 and out[i].shape == one["audio"][0].shape, i
+        tol = _i16_tol(one["pcm"][0])
+        assert np.abs(out[i].astype(np.int32) - one["audio"][0].astype(np.int32)).max() <= tol, i
+        assert np.array_equal(streamed[i], out[i]), i  # same plan, same seeds, noise off: identical runs

@@ -7,22 +7,28 @@
 // Operand images.  Both MMA operands are K-major, SWIZZLE_NONE with SBO = 128 B, i.e. [k-chunk of 8][row][8 bf16]:
 // the address is linear in the row, so conv tap k is the SAME activation image with the descriptor start address
 // advanced by k*dil rows (16 B each) — no im2col, no per-tap copies.
-//   * weights: pre-split bf16 image per (n-tile, ci-chunk, tap), one cp.async.bulk (TMA engine) per stage;
+//   * weights: pre-split bf16 image per (n-tile, ci-chunk, tap) with the hi/lo(/lo2) planes of a k-chunk as adjacent
+//     row blocks: one cp.async.bulk (TMA engine) per ring slot, and ONE MMA with N = 2*NT (3*NT) multiplies an
+//     activation plane with all weight planes at once (an SS-mode MMA re-reads its A block from shared memory, so
+//     fewer, wider MMAs are what narrow layers need);
 //   * activations, "plane" mode: the PRODUCING layer's epilogue already wrote the bf16 hi/lo planes of its
 //     (pre-activated) output in image order [plane][C/8][PADL + rows][8] to global memory, so the consumer's A
 //     tile is 2*4 contiguous bulk copies per 32-channel chunk — no SM instructions on the operand path;
-//   * activations, "gather" mode (inputs produced by non-conv kernels, or needing the MRF mean of 3 tensors):
-//     warps 0..7 read fp32 [C][L], apply the pre-op, split and write the image to smem themselves.
+//   * activations, "gather" mode (inputs produced by non-conv kernels): the epilogue warps read fp32 [C][L], apply the
+//     pre-op, split and write the image to smem themselves.
 //
-// One CTA (320 threads):
-//   warps 0..7 : gather-mode A producers during the main loop; afterwards the epilogue:
-//                TMEM -> registers (tcgen05.ld 32x32b) -> bias / act / residual / tanh*sigmoid gate / WN res-skip /
-//                affine coupling + InvConvNear^-1 + ActNorm^-1 / pixel shuffle -> fp32 [C][L] (+ bf16 planes for the
-//                next conv, including the zero rows that implement the reference's padding/masking);
-//   warp 8     : MMA issuer (one lane): tcgen05.mma.cta_group::1.kind::f16, one accumulator per magnitude class;
-//   warp 9     : lane 0 weight bulk copies; (plane mode) thread 0 issues the activation bulk copies.
-// Pipelines: A ring (2 stages, per ci-chunk of 32 channels, reused by all K taps), W ring (3 stages, per tap),
-// accumulator barrier (MMA -> epilogue).  All waits are mbarrier based; tcgen05.commit releases stages.
+// One CTA = EW*32 + 64 (+32) threads:
+//   warps 0..EW-1 : gather-mode A producers during the main loop; otherwise the epilogue:
+//                   TMEM -> registers (tcgen05.ld 32x32b) -> bias / act / residual / tanh*sigmoid gate / WN res-skip /
+//                   affine coupling + InvConvNear^-1 + ActNorm^-1 / pixel shuffle -> fp32 [C][L] and/or the bf16 planes
+//                   of the next conv (including the zero rows that implement the reference's padding/masking);
+//   warp EW       : MMA issuer (one elected lane): tcgen05.mma.cta_group::1.kind::f16, one accumulator per magnitude class;
+//   warp EW+1     : lane 0: weight bulk copies;
+//   warp EW+2     : (NBUF = 2 only) lane 0: activation bulk copies; with NBUF = 1 thread 0 issues them for its one tile.
+// Pipelines: A ring (AST stages, per ci-chunk of 32 channels, reused by all K taps), W ring (WST slots of G taps),
+// accumulator full/empty barriers per TMEM buffer (NBUF = 2: the MMA warp fills one buffer while the epilogue warps drain
+// the other and the rings run ahead into the CTA's next time tile).  All waits are mbarrier based; tcgen05.commit
+// releases stages.
 #pragma once
 #include "common.cuh"
 #include "umma.cuh"

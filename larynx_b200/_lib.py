@@ -1,7 +1,6 @@
 """ctypes binding of libb200tts.so (include/b200tts.h).  Fails loudly — there is no fallback."""
 from __future__ import annotations
 
-import ctypes
 import ctypes as C
 import os
 import threading

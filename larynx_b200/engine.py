@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 import threading
-from typing import Dict, Optional, Sequence
+from typing import Dict, Sequence
 
 import numpy as np
 

@@ -19,7 +19,7 @@ so it also checks the product's weight-norm folding / InvConv pre-inversion.
 from __future__ import annotations
 
 import math
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, Optional
 
 import numpy as np
 import torch

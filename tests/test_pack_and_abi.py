@@ -7,7 +7,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from larynx_b200 import _lib, pack, synth
+from larynx_b200 import _lib, pack
 from tests import common
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -144,3 +144,45 @@ def test_denoiser_restatements_equal_reference():
         m, p = la.transform(audio)
         r = la.inverse(np.clip(m - bias * 0.7, 0, None), p)
         assert np.abs(r - a).max() < 1e-12
+
+
+def test_glue_variants_host_mirror_oracle_and_reference_agree():
+    """Every AudioSettings combination the glue can take (larynx/audio.py:58-59,83-108): the product's host mirror
+    (larynx_b200.host.MelGlue, used between the two boundary calls), the oracle restatement, and the reference's own
+    AudioSettings where it can be imported."""
+    from larynx_b200 import host
+
+    m = np.random.RandomState(5).uniform(-5, 5, size=(1, 80, 37)).astype(np.float32)
+    la = None
+    if ref_harness.available():
+        ref_harness.import_reference()
+        import larynx.audio as la  # noqa: F811
+    for signal_norm in (False, True):
+        for symmetric in (True, False):
+            for clip in (True, False):
+                for db2amp, drc in ((True, True), (True, False), (False, True)):
+                    cfg = dict(common.glow_cfg()["audio"])
+                    cfg.update(signal_norm=signal_norm, symmetric_norm=symmetric, clip_norm=clip, convert_db_to_amp=db2amp,
+                               do_dynamic_range_compression=drc, max_norm=4.0, min_level_db=-100.0, ref_level_db=20.0,
+                               spec_gain=20.0 if signal_norm else 1.0)
+                    x = m if signal_norm else m * 0.2  # keep 10**x finite without normalisation
+                    a = host.MelGlue.from_config(cfg).apply(x)
+                    b = port.mel_glue(x, cfg)
+                    assert a.dtype == np.float32 and np.array_equal(a, b), cfg
+                    if la is not None:
+                        s = la.AudioSettings(**{k: v for k, v in cfg.items() if k in la.AudioSettings.__dataclass_fields__})
+                        r = x
+                        if s.signal_norm and not s.clip_norm:
+                            # reference bug: denormalize() only binds its result inside `if self.clip_norm`
+                            # (larynx/audio.py:87-91) and raises; no shipped voice has clip_norm false.  The product
+                            # and the oracle treat it as "no clipping".
+                            with pytest.raises(UnboundLocalError):
+                                s.denormalize(r)
+                            continue
+                        if s.signal_norm:
+                            r = s.denormalize(r)
+                        if s.convert_db_to_amp:
+                            r = s.db_to_amp(r)
+                        if s.do_dynamic_range_compression:
+                            r = s.dynamic_range_compression(r)
+                        assert np.allclose(a, r, rtol=1e-6, atol=1e-6), cfg

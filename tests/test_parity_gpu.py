@@ -386,3 +386,26 @@ def test_batch_scheduler_matches_per_sentence_results():
         tol = _i16_tol(one["pcm"][0])
         assert np.abs(out[i].astype(np.int32) - one["audio"][0].astype(np.int32)).max() <= tol, i
         assert np.array_equal(streamed[i], out[i]), i  # same plan, same seeds, noise off: identical runs
+
+
+@pytest.mark.parametrize("over", [
+    dict(signal_norm=True, symmetric_norm=True, clip_norm=True, spec_gain=20.0),
+    dict(signal_norm=True, symmetric_norm=False, clip_norm=True, spec_gain=20.0),
+    dict(signal_norm=False, convert_db_to_amp=True, do_dynamic_range_compression=False, spec_gain=1.0),
+    dict(signal_norm=False, convert_db_to_amp=False, do_dynamic_range_compression=True),
+])
+def test_device_glue_variants_match_host_glue(over):
+    """The glue inside b200tts_tts_finish (struct b200tts_glue) against the numpy glue of the two-call path
+    (larynx/__init__.py:242-249) for AudioSettings other than ljspeech's."""
+    glow, voc = common.product_glow(), common.product_hifi()
+    cfg = dict(common.glow_cfg()["audio"])
+    cfg.update(max_norm=4.0, min_level_db=-100.0, ref_level_db=20.0)
+    cfg.update(over)
+    glue = host.MelGlue.from_config(cfg)
+    ids = synth.bench_ids(24, seed=77)
+    eps = synth.seeded_eps(512, seed=3)
+    f = host.synthesize_batch(glow, voc, glue, [ids], 0.667, 1.0, eps=eps[None], want_float=True, want_mel=True)
+    two_call = voc.mels_to_float(glue.apply(f["mel"][0][None]))
+    assert f["pcm"][0].shape == two_call.shape
+    assert np.all(np.isfinite(two_call))
+    assert np.abs(f["pcm"][0] - two_call).max() <= 20 * TOL_PCM

@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import typing
 from abc import ABC
-from dataclasses import dataclass
+from dataclasses import field, make_dataclass
 from enum import Enum
 from pathlib import Path
 
@@ -32,37 +32,29 @@ except Exception:  # noqa: BLE001 - larynx (or one of its imports) is not availa
     ARRAY_OR_TENSOR = typing.Union[np.ndarray, typing.Any]
     SettingsType = typing.Dict[str, typing.Any]
 
-    class InferenceBackend(str, Enum):
-        ONNX = "onnx"
-        PYTORCH = "pytorch"
+    InferenceBackend = Enum("InferenceBackend", {"ONNX": "onnx", "PYTORCH": "pytorch"}, type=str)
 
-    @dataclass
-    class TextToSpeechModelConfig:
-        model_path: Path
-        session_options: typing.Any = None
-        use_cuda: bool = True
-        half: bool = True
-        backend: typing.Optional[InferenceBackend] = None
+    # fields shared by both config records, in the reference's positional order (larynx/constants.py:51-59, 78-87)
+    _COMMON = [("model_path", Path), ("session_options", typing.Any, field(default=None)),
+               ("use_cuda", bool, field(default=True)), ("half", bool, field(default=True))]
+    _BACKEND = ("backend", typing.Optional[InferenceBackend], field(default=None))
+    TextToSpeechModelConfig = make_dataclass("TextToSpeechModelConfig", _COMMON + [_BACKEND])
+    VocoderModelConfig = make_dataclass("VocoderModelConfig", _COMMON + [("denoiser_strength", float, field(default=0.0)), _BACKEND])
 
     class TextToSpeechModel(ABC):
-        def __init__(self, config: TextToSpeechModelConfig):
-            pass
+        """phoneme ids -> mel spectrogram (larynx/constants.py:62-72)."""
 
-        def phonemes_to_mels(self, phoneme_ids: np.ndarray, settings: typing.Optional[SettingsType] = None) -> ARRAY_OR_TENSOR:
-            pass
+        def __init__(self, config):
+            self._config = config
 
-    @dataclass
-    class VocoderModelConfig:
-        model_path: Path
-        session_options: typing.Any = None
-        use_cuda: bool = True
-        half: bool = True
-        denoiser_strength: float = 0.0
-        backend: typing.Optional[InferenceBackend] = None
+        def phonemes_to_mels(self, phoneme_ids, settings=None):
+            raise NotImplementedError
 
     class VocoderModel(ABC):
-        def __init__(self, config: VocoderModelConfig):
-            pass
+        """mel spectrogram -> int16 audio (larynx/constants.py:90-100)."""
 
-        def mels_to_audio(self, mels: ARRAY_OR_TENSOR, settings: typing.Optional[SettingsType] = None) -> np.ndarray:
-            pass
+        def __init__(self, config):
+            self._config = config
+
+        def mels_to_audio(self, mels, settings=None):
+            raise NotImplementedError

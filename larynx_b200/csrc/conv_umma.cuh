@@ -497,289 +497,7 @@ __global__ void __launch_bounds__(EW * 32 + 64 + (NBUF == 2 ? 32 : 0), EW == 8 ?
     const uint32_t tm = tmem + (uint32_t)buf * (ACC_COLS * NT);
     if (tid == 0 && it == 0) UM_TRACE(6);
     if (tid == 0 && it < 8) UM_TRACE(16 + it * 4 + 2);
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may read
-    const int wset = warp >> 2; // EW/4 warp sets share the (M tile, 32-column group) tasks round robin
-    constexpr int NWS = EW / 4;
-    const int m = quad * 32 + lane;
-    const int ngroups = (NT + 31) / 32;
-    const int u = p.pix > 1 ? p.pix : 1;
-    // plane outputs: primary (yp) and, for EPI_RESSKIP, the skip accumulator (yp2)
-    PlaneOut po, po2;
-    po.base = p.yp ? reinterpret_cast<unsigned char*>(p.yp) + (size_t)b * p.yp_bs : nullptr;
-    po.kc_total = p.yp_kc; po.rows = p.yp_rows; po.nsplit = p.yp_nsplit; po.slope = p.yp_slope;
-    po.tail_row0 = (long long)UM_PADL + (long long)(t0 + MT * 128) * u;
-
-    for (int task = wset; task < MT * ngroups; task += NWS) {
-      const int mt = MT == 1 ? 0 : task % MT;  // task = g * MT + mt
-      const int g = MT == 1 ? task : task / MT;
-      const int t = t0 + mt * 128 + m;
-      const bool t_ok = t < Lb;
-      po.pad_front = mtile == 0;
-      po.pad_tail = (long long)(t0 + MT * 128) >= Lb;
-      po.m = mt * 128 + m;
-      po2 = po;
-      po2.base = p.yp2 ? reinterpret_cast<unsigned char*>(p.yp2) + (size_t)b * p.yp_bs : nullptr;
-      float acc[32];
-      {
-        uint32_t raw[32];
-        const uint32_t lane_addr = tm + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * 32);
-        tmem_ld32(lane_addr + (uint32_t)((mt * NACC + NACC - 1) * NT), raw);  // smallest magnitude class first
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(raw[j]);
-#pragma unroll
-        for (int a = NACC - 2; a >= 0; --a) {
-          tmem_ld32(lane_addr + (uint32_t)((mt * NACC + a) * NT), raw);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(raw[j]);
-        }
-      }
-      const int nb = n0 + g * 32;  // packed channel of acc[0]
-      const int jmax = min(32, min(NT - g * 32, p.Cout - nb));
-      if (jmax <= 0) continue;
-      if (tid == 0 && task == wset && it == 0) UM_TRACE(9);
-      if (p.epi == EPI_PLAIN && u == 1) {
-        float* __restrict__ yb = p.y + (size_t)b * p.y_bs + t;
-        float rv[32];
-        if (p.rp) {
-          // residual from the hi/lo image of the block input (16 significant bits; 8 channels per 16-byte load)
-          const unsigned char* rb = reinterpret_cast<const unsigned char*>(p.rp) + (size_t)b * p.rp_bs;
-          const size_t pstride = (size_t)p.rp_kc * p.rp_rows * 16;
-          const long long row = (long long)UM_PADL + (t_ok ? t : 0);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int kc = (nb >> 3) + (q * 8 < jmax ? q : 0);
-            const unsigned char* a = rb + ((size_t)kc * p.rp_rows + row) * 16;
-            const uint4 h = *reinterpret_cast<const uint4*>(a), l = *reinterpret_cast<const uint4*>(a + pstride);
-            const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float v0 = __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
-              const float v1 = __uint_as_float(hw[e] & 0xffff0000u) + __uint_as_float(lw[e] & 0xffff0000u);
-              rv[q * 8 + 2 * e] = v0 > 0.f ? v0 : v0 * p.rp_inv_slope;
-              rv[q * 8 + 2 * e + 1] = v1 > 0.f ? v1 : v1 * p.rp_inv_slope;
-            }
-          }
-        } else if (p.res && t_ok) {
-          const float* __restrict__ rb = p.res + (size_t)b * p.res_bs + t;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) rv[j] = rb[(size_t)(nb + (j < jmax ? j : 0)) * p.res_ld];
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) rv[j] = 0.f;
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float v = acc[j] + s_bias[g * 32 + j];
-          if (p.act == ACT_RELU) v = fmaxf(v, 0.f);
-          else if (p.act == ACT_TANH) v = tanhf(v);
-          v += rv[j];
-          acc[j] = (t_ok && j < jmax) ? v : 0.f;
-        }
-        if (t_ok && p.y) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < jmax) yb[(size_t)(nb + j) * p.y_ld] = acc[j];
-        }
-        if (po.base) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if (q * 8 < jmax) plane_store8(po, (nb >> 3) + q, (long long)UM_PADL + t, acc + q * 8);
-        }
-      } else if (p.epi == EPI_PLAIN) {
-        // pixel shuffle (transposed conv): packed channel n = co*u + r -> y[co][t*u + r]
-        float* __restrict__ yb = p.y + (size_t)b * p.y_bs;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j] = (t_ok && j < jmax) ? acc[j] + s_bias[g * 32 + j] : 0.f;
-        if (t_ok) {
-          if (u == 8 && jmax == 32) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float4* d = reinterpret_cast<float4*>(yb + (size_t)(nb / 8 + q) * p.y_ld + (size_t)t * 8);
-              d[0] = make_float4(acc[q * 8 + 0], acc[q * 8 + 1], acc[q * 8 + 2], acc[q * 8 + 3]);
-              d[1] = make_float4(acc[q * 8 + 4], acc[q * 8 + 5], acc[q * 8 + 6], acc[q * 8 + 7]);
-            }
-          } else if (u == 4 && jmax == 32) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-              *reinterpret_cast<float4*>(yb + (size_t)(nb / 4 + q) * p.y_ld + (size_t)t * 4) =
-                  make_float4(acc[q * 4 + 0], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]);
-          } else if (u == 2 && jmax == 32) {
-#pragma unroll
-            for (int q = 0; q < 16; ++q)
-              *reinterpret_cast<float2*>(yb + (size_t)(nb / 2 + q) * p.y_ld + (size_t)t * 2) = make_float2(acc[q * 2], acc[q * 2 + 1]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (j < jmax) {
-                const int n = nb + j, co = n / u, r = n - co * u;
-                yb[(size_t)co * p.y_ld + (size_t)t * u + r] = acc[j];
-              }
-            }
-          }
-        }
-        if (po.base && jmax == 32) {
-          const long long orow = (long long)UM_PADL + (long long)t * u;
-          if (u == 2) {  // 16 channels x 2 phases: two full chunks per output row
-#pragma unroll
-            for (int r = 0; r < 2; ++r)
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                float v8[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v8[e] = acc[(h * 8 + e) * 2 + r];
-                PlaneOut pr = po;  // the zero rows are emitted once, with phase 0
-                if (r) pr.pad_front = pr.pad_tail = false;
-                plane_store8(pr, (nb >> 4) + h, orow + r, v8);
-              }
-          } else if (u == 4) {  // 8 channels x 4 phases
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-              float v8[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v8[e] = acc[e * 4 + r];
-              PlaneOut pr = po;
-              if (r) pr.pad_front = pr.pad_tail = false;
-              plane_store8(pr, nb >> 5, orow + r, v8);
-            }
-          } else if (u == 8) {  // 4 channels x 8 phases: half chunks
-            const int co0 = nb >> 3;
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-              float v4[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) v4[e] = acc[e * 8 + r];
-              plane_store4(po, co0 >> 3, (co0 & 7) * 2, orow + r, v4);
-            }
-            const uint2 z = make_uint2(0, 0);  // zero rows for this half chunk
-            for (int pl = 0; pl < po.nsplit; ++pl) {
-              if (po.pad_front && po.m < UM_PADL) *reinterpret_cast<uint2*>(po.at(pl, co0 >> 3, po.m) + (co0 & 7) * 2) = z;
-              if (po.pad_tail && po.m < UM_TAIL) *reinterpret_cast<uint2*>(po.at(pl, co0 >> 3, po.tail_row0 + po.m) + (co0 & 7) * 2) = z;
-            }
-          }
-        }
-      } else if (p.epi == EPI_GATE) {
-        float* __restrict__ yb = p.y + (size_t)b * p.y_bs + t;
-        float o16[16];
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          const float a = acc[j] + s_bias[g * 32 + j];
-          const float gt = acc[j + 1] + s_bias[g * 32 + j + 1];
-          // tanh(a) = 1 - 2/(e^{2a}+1), sigmoid(g) = 1/(1+e^{-g}) with ex2.approx / fast division (~2 ulp each):
-          // absolute error ~1e-7, far inside the bf16-split error budget of this path
-          const float th = 1.f - __fdividef(2.f, __expf(2.f * a) + 1.f);
-          const float sg = __fdividef(1.f, 1.f + __expf(-gt));
-          const float v = th * sg;
-          o16[j >> 1] = (t_ok && j < jmax) ? v : 0.f;
-        }
-        if (t_ok && p.y) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (2 * j < jmax) yb[(size_t)((nb >> 1) + j) * p.y_ld] = o16[j];
-        }
-        if (po.base) {
-#pragma unroll
-          for (int q = 0; q < 2; ++q)
-            if (q * 16 < jmax) plane_store8(po, (nb >> 4) + q, (long long)UM_PADL + t, o16 + q * 8);
-        }
-      } else if (p.epi == EPI_RESSKIP) {
-        // a 32-channel group lies entirely on one side of `split` (split is a multiple of 32)
-        const bool in_y = nb < p.split;
-        float* db = in_y ? p.y + (size_t)b * p.y_bs + (size_t)nb * p.y_ld + t
-                         : p.aux + (size_t)b * p.aux_bs + (size_t)(nb - p.split) * p.aux_ld + t;
-        const int ld = in_y ? p.y_ld : p.aux_ld;
-        const bool load_old = t_ok && (in_y || !p.first);
-        float old[32];
-        if (load_old) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) old[j] = db[(size_t)(j < jmax ? j : 0) * ld];
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) old[j] = 0.f;
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j] = (t_ok && j < jmax) ? old[j] + (acc[j] + s_bias[g * 32 + j]) : 0.f;
-        if (tid == 0 && task == wset && it == 0) UM_TRACE(10);
-        if (t_ok) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < jmax) db[(size_t)j * ld] = acc[j];
-        }
-        if (tid == 0 && task == wset && it == 0) UM_TRACE(11);
-        const PlaneOut& pp = in_y ? po : po2;
-        if (pp.base) {
-          const int c0 = in_y ? nb : nb - p.split;
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if (q * 8 < jmax) plane_store8(pp, (c0 >> 3) + q, (long long)UM_PADL + t, acc + q * 8);
-        }
-      } else {  // EPI_COUPLING (+ InvConvNear^-1 + ActNorm^-1), see conv1d.cuh for the channel algebra
-        float* sb = p.y + (size_t)b * p.y_bs + t;
-        const float* s0 = t_ok ? sb : p.y;  // safe address for masked rows
-        const int half = p.half;
-        float xin[32];  // per group of 4 packed channels: x0[2q], x0[2q+1], x1[2q], x1[2q+1]
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const int i0 = (t_ok && j < jmax) ? (nb + j) >> 1 : 0;
-          xin[j + 0] = s0[(size_t)i0 * p.y_ld];
-          xin[j + 1] = s0[(size_t)(i0 + 1) * p.y_ld];
-          xin[j + 2] = s0[(size_t)(half + i0) * p.y_ld];
-          xin[j + 3] = s0[(size_t)(half + i0 + 1) * p.y_ld];
-        }
-        float wi[16];
-#pragma unroll
-        for (int o = 0; o < 16; ++o) wi[o] = s_inv[o];
-        float zo[32];  // [j..j+3] = new state channels (2q, 2q+1, half+2q, half+2q+1)
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const int i0 = (j < jmax) ? (nb + j) >> 1 : 0;
-          const int ch[4] = {i0, i0 + 1, half + i0, half + i0 + 1};
-          float vin[4];
-          vin[0] = xin[j + 0];
-          vin[1] = xin[j + 1];
-          vin[2] = (xin[j + 2] - (acc[j] + s_bias[g * 32 + j])) * __expf(-(acc[j + 1] + s_bias[g * 32 + j + 1]));
-          vin[3] = (xin[j + 3] - (acc[j + 2] + s_bias[g * 32 + j + 2])) * __expf(-(acc[j + 3] + s_bias[g * 32 + j + 3]));
-#pragma unroll
-          for (int o = 0; o < 4; ++o) {
-            float z = wi[o * 4 + 0] * vin[0];
-            z = fmaf(wi[o * 4 + 1], vin[1], z);
-            z = fmaf(wi[o * 4 + 2], vin[2], z);
-            z = fmaf(wi[o * 4 + 3], vin[3], z);
-            z = (z - s_anb[ch[o]]) * s_ans[ch[o]];
-            zo[j + o] = (t_ok && j < jmax) ? z : 0.f;
-          }
-        }
-        if (t_ok) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (j < jmax) {
-              const int i0 = (nb + j) >> 1;
-              sb[(size_t)i0 * p.y_ld] = zo[j];
-              sb[(size_t)(i0 + 1) * p.y_ld] = zo[j + 1];
-              sb[(size_t)(half + i0) * p.y_ld] = zo[j + 2];
-              sb[(size_t)(half + i0 + 1) * p.y_ld] = zo[j + 3];
-            }
-          }
-        }
-        if (po.base) {
-          // 32 packed columns = 8 q's = state channels [nb/2, nb/2+16) of both halves: 2 chunks each
-#pragma unroll
-          for (int hh = 0; hh < 2; ++hh)
-#pragma unroll
-            for (int q2 = 0; q2 < 2; ++q2) {
-              if (q2 * 16 >= jmax) continue;
-              float v8[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const int i = q2 * 8 + e;  // channel offset inside the 16-channel run
-                v8[e] = zo[(i >> 1) * 4 + hh * 2 + (i & 1)];
-              }
-              plane_store8(po, ((hh * half + (nb >> 1)) >> 3) + q2, (long long)UM_PADL + t, v8);
-            }
-        }
-      }
-    }
+#include "conv_umma_epilogue.inc"
     // this warp is done reading the accumulator buffer: hand it back to the MMA warp
     tc_fence_before();
     __syncwarp();

@@ -305,6 +305,11 @@ static bool mean_image() {
   static const bool on = getenv("B200TTS_NO_MEAN_IMAGE") == nullptr;
   return on;
 }
+// Round-2 work in progress (conv_chain.cuh): the flow decoder's convs in one cooperative launch.  Off by default.
+static bool flow_chain() {
+  static const bool on = getenv("B200TTS_FLOW_CHAIN") != nullptr;
+  return on;
+}
 static bool conv_trace() {
   static const bool on = getenv("B200TTS_CONV_TRACE") != nullptr;
   return on;
@@ -602,6 +607,9 @@ static void glow_flow_impl(const b200tts_glow* m, b200tts_call* c, float noise_s
   if (um) need += Arena::pad(B * plane_item_bytes(C, prow, 2), 1) + 3 * Arena::pad(B * plane_item_bytes(Hd, prow, 2), 1);
   if (eps_host) need += Arena::pad((size_t)B * mel * eps_ld, 4);
   if (c->debug) need += Arena::pad((size_t)m->n_blocks * B * C * ldq, 4);
+  const bool chaining = flow_chain() && um && !c->debug && !conv_trace();
+  const size_t chain_cap = (size_t)m->n_blocks * (2 + 2 * m->n_block_layers);
+  if (chaining) need += Arena::pad(chain_cap * sizeof(ConvParams), 1) + Arena::pad(chain_cap, 4);
   c->dec.reserve(need + extra_bytes + 4096);
   c->idx_d = c->dec.take<int>(B * c->idx_ld);
   float* S = c->dec.take<float>((size_t)B * C * ldq);
@@ -640,6 +648,19 @@ static void glow_flow_impl(const b200tts_glow* m, b200tts_call* c, float noise_s
     p.lens = lens; p.len_mul = 1; p.Lin = Tq;
     return p;
   };
+  // chaining (B200TTS_FLOW_CHAIN=1): every conv after the first (which gathers fp32) is recorded and all of them run
+  // in one cooperative launch at the end
+  std::vector<ConvParams> chain;
+  auto run = [&](ConvParams& p, const ConvW& w) {
+    if (chaining && w.wu && p.xp) {
+      p.w = w.w; p.bias = w.b; p.Cin = w.cin; p.Cout = w.cout; p.K = w.k;
+      p.wu = w.wu; p.um_nt = w.nt; p.um_nsplit = w.nsplit;
+      chain.push_back(p);
+    } else {
+      B2_CHECK(chain.empty(), "flow chain: a layer without operand images in the middle of the chain");
+      conv(c, p, w, batch, Tq, s);
+    }
+  };
   for (int blk = m->n_blocks - 1; blk >= 0; --blk) {
     const GlowFlow& f = m->flow[blk];
     // CouplingBlock reverse                                     attentions.py:119-142
@@ -648,7 +669,7 @@ static void glow_flow_impl(const b200tts_glow* m, b200tts_call* c, float noise_s
       if (blk != m->n_blocks - 1) set_in(p, S_p);  // the first state comes from the expand kernel (fp32 gather)
       set_out(p, H_p, 1.f);
     }
-    conv(c, p, f.start, batch, Tq, s);
+    run(p, f.start);
     for (int l = 0; l < m->n_block_layers; ++l) {  // WN       layers.py:138-162
       int dil = 1;
       for (int j = 0; j < l; ++j) dil *= m->dil_rate;
@@ -659,7 +680,7 @@ static void glow_flow_impl(const b200tts_glow* m, b200tts_call* c, float noise_s
         set_out(p, A_p, 1.f);
         p.y = nullptr;  // the gate output is only ever read as an MMA operand
       }
-      conv(c, p, f.in[l], batch, Tq, s);
+      run(p, f.in[l]);
       p = mk(ACT, Hd, Hh, Hd);
       p.epi = EPI_RESSKIP; p.aux = SK; p.aux_bs = (long long)Hd * ldq; p.aux_ld = ldq;
       p.split = l < m->n_block_layers - 1 ? Hd : 0;
@@ -668,7 +689,7 @@ static void glow_flow_impl(const b200tts_glow* m, b200tts_call* c, float noise_s
         set_in(p, A_p);
         set_out(p, H_p, 1.f, &K_p);
       }
-      conv(c, p, f.rs[l], batch, Tq, s);
+      run(p, f.rs[l]);
     }
     p = mk(SK, Hd, S, C);
     p.epi = EPI_COUPLING; p.inv_w = f.inv; p.an_bias = f.an_bias; p.an_scale = f.an_scale; p.half = C / 2;
@@ -676,10 +697,22 @@ static void glow_flow_impl(const b200tts_glow* m, b200tts_call* c, float noise_s
       set_in(p, K_p);
       set_out(p, S_p, 1.f);
     }
-    conv(c, p, f.end, batch, Tq, s);
+    run(p, f.end);
     if (c->taps_d)
       B2_CUDA(cudaMemcpyAsync(c->taps_d + (size_t)blk * B * C * ldq, S, sizeof(float) * B * C * ldq,
                               cudaMemcpyDeviceToDevice, s));
+  }
+  if (!chain.empty()) {
+    const int n = (int)chain.size();
+    if (conv_chain_supported(chain.data(), n, batch, Tq)) {
+      B2_CHECK((size_t)n <= chain_cap, "flow chain longer than its workspace");
+      ConvParams* layers_d = reinterpret_cast<ConvParams*>(c->dec.take<unsigned char>(chain_cap * sizeof(ConvParams)));
+      unsigned int* counter_d = c->dec.take<unsigned int>(chain_cap);
+      B2_CUDA(cudaMemcpyAsync(layers_d, chain.data(), sizeof(ConvParams) * n, cudaMemcpyHostToDevice, s));
+      c->launches += launch_conv_chain(chain.data(), layers_d, n, counter_d, batch, Tq, s);
+    } else {  // too many CTAs for a cooperative launch (large batches): one launch per layer as usual
+      for (ConvParams& q : chain) c->launches += launch_conv_umma(q, batch, Tq, s);
+    }
   }
 }
 

@@ -61,4 +61,10 @@ void launch_mean3_image(const float* x1, const float* x2, const float* x3, long 
                         const int* lens, int len_mul, int batch, void* img, long long img_bs, int kc_total, int rows,
                         cudaStream_t s);
 
+// chained convs in one cooperative launch (conv_chain.cu; round-2 work in progress, off unless B200TTS_FLOW_CHAIN=1)
+void conv_chain_init_attributes();
+bool conv_chain_supported(const ConvParams* layers, int n_layers, int batch, int Lmax);
+int launch_conv_chain(const ConvParams* layers, const ConvParams* layers_d, int n_layers, unsigned int* counter_d, int batch,
+                      int Lmax, cudaStream_t s);
+
 }  // namespace b2

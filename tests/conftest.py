@@ -28,3 +28,14 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def built_library():
+    """libb200tts.so is a build artefact (git-ignored): a fresh checkout compiles it once (nvcc cross-compiles sm_100a
+    without a GPU) so that the ABI tests do not depend on a previous `python -m larynx_b200.build`."""
+    from larynx_b200 import _lib, build
+
+    if not _lib.lib_path().exists():
+        build.build()
+    return _lib.load()

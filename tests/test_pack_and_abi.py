@@ -95,20 +95,20 @@ def test_synth_param_counts():
     assert n_folded == 13_926_017
 
 
-def test_library_exports_every_declared_symbol():
+def test_library_exports_every_declared_symbol(built_library):
     header = open(os.path.join(ROOT, "include", "b200tts.h")).read()
     declared = set(re.findall(r"\b(b200tts_[a-z0-9_]+)\s*\(", header))
     declared -= {"b200tts_call_set_debug(call,1)"}
     assert len(declared) >= 20
-    lib = _lib.load()
+    lib = built_library
     for name in declared:
         assert hasattr(lib, name), f"libb200tts.so does not export {name}"
     assert set(_lib.EXPORTED_SYMBOLS) == declared
     assert lib.b200tts_version() == 1
 
 
-def test_fails_loudly_without_device_or_with_bad_blob():
-    lib = _lib.load()
+def test_fails_loudly_without_device_or_with_bad_blob(built_library):
+    lib = built_library
     try:
         ngpu = torch.cuda.device_count()
     except Exception:  # noqa: BLE001

@@ -77,6 +77,7 @@ struct ConvParams {
   const float* an_bias = nullptr;   // [2*half]
   const float* an_scale = nullptr;  // [2*half] = exp(-logs)
   int half = 0;                     // channels per coupling half (80)
+  float* tap = nullptr;             // optional copy of the updated flow state (same layout as y; debug taps)
   // tensor-core path (conv_umma.cuh): pre-split bf16 weight image, N tile, split count, pixel-shuffle factor
   const void* wu = nullptr;
   int um_nt = 0, um_nsplit = 2, pix = 1;

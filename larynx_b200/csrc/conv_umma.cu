@@ -1,6 +1,4 @@
 // conv_umma.cu — launcher of the tcgen05 implicit-GEMM conv (conv_umma.cuh).
-#include <stdlib.h>
-
 #include <algorithm>
 
 #include "conv_umma.cuh"
@@ -89,16 +87,16 @@ int launch_conv_umma_batch(const ConvParams* ps, int n, int batch, int Lmax, cud
   const ConvParams& p = ps[0];
   const int ntiles = (p.Cout + p.um_nt - 1) / p.um_nt;
   const long long ctas1 = (long long)((Lmax + 127) / 128) * ntiles * batch * n;
-  // tuning knobs (thread-safe one-time init).  Narrow layers with very many time tiles (HiFi-GAN stages 3 and 4) are
-  // bound by per-CTA set-up and by re-streaming the weights for every 128 rows: taller tiles amortise both.
-  static const long long mt_min = [] { const char* e = getenv("B200TTS_MT_MIN"); return e ? atoll(e) : 149LL; }();
-  static const long long ew16_max = [] { const char* e = getenv("B200TTS_EW16_MAX"); return e ? atoll(e) : 148LL; }();
+  // Tuned constants (profiles/r1_tcgen05_summary.md).  Narrow layers with very many time tiles (HiFi-GAN stages 3 and 4)
+  // are bound by per-CTA set-up and by re-streaming the weights for every 128 rows: taller tiles amortise both.
+  constexpr long long mt_min = 149;    // grids from this many 128-row CTAs on take the taller-tile variants
+  constexpr long long ew16_max = 148;  // grids up to this size use the 16-epilogue-warp variants (one CTA per SM)
   // Persistent launch: one CTA per SM; the 148 CTAs are split between the convs (branches) of the launch in proportion
   // to their cost per tile, max(mainloop ~ K * input chunks, epilogue), and each CTA walks the time tiles of its
   // (n-tile, item, branch) with a stride of gx[branch].
-  static const int persist_min = [] { const char* e = getenv("B200TTS_PERSIST_MIN"); return e ? atoi(e) : 3; }();
-  static const int persist_ctas = [] { const char* e = getenv("B200TTS_PERSIST_CTAS"); return e ? atoi(e) : 148; }();
-  static const int epi_units = [] { const char* e = getenv("B200TTS_EPI_UNITS"); return e ? atoi(e) : 15; }();
+  constexpr int persist_min = 3;       // tiles per CTA from which a persistent launch pays
+  constexpr int persist_ctas = 148;
+  constexpr int epi_units = 15;        // epilogue cost of a tile in units of one (tap, 32-channel chunk) of main loop
   const long long per = (long long)ntiles * batch;
   if (p.um_nsplit == 2 && p.xp != nullptr && per * n <= persist_ctas) {
     const int mt = p.um_nt <= 32 && p.Cin <= 32 ? 4 : (p.um_nt <= 64 ? 2 : 1);
@@ -170,8 +168,9 @@ __global__ void __launch_bounds__(256) mean3_image_kernel(const float* __restric
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     const size_t off = base + (size_t)e * ld;
-    float a = (x1[off] + x2[off]) + x3[off];
-    a = a / div;
+    float a = x1[off];
+    if (x2) a = (a + x2[off]) + x3[off];  // x2 and x3 come together (MRF mean); alone: the image of x1 itself
+    if (div != 1.f) a = a / div;
     a = a > 0.f ? a : a * slope;
     v[e] = ok ? a : 0.f;
   }

@@ -15,6 +15,7 @@
 #include <string>
 #include <vector>
 
+#include "flow_chain_params.cuh"
 #include "kernels.cuh"
 
 using namespace b2;
@@ -126,6 +127,11 @@ struct b200tts_glow {
   const float *pre_lng[3], *pre_lnb[3], *dp_ln1g, *dp_ln1b, *dp_ln2g, *dp_ln2b, *dp_pw, *dp_pb;
   std::vector<GlowEnc> enc;
   std::vector<GlowFlow> flow;
+  // persistent flow-decoder kernel (flow_chain.cuh): the blocks' weights in execution order, nullptr if the geometry
+  // is not the one the kernel is built for
+  FlowBlockDev* flow_dev = nullptr;
+  int flow_nt_end = 0;
+  ~b200tts_glow() { cudaFree(flow_dev); }
 };
 
 struct HifiRB {
@@ -288,30 +294,29 @@ static void set_out(ConvParams& p, const Planes& pl, float slope, const Planes* 
   if (second) p.yp2 = second->ptr;
 }
 
-// B200TTS_CONV=simt selects the fp32 SIMT cross-check path everywhere; default: tcgen05 where a weight image exists.
-// (function-local statics: initialised once, thread-safe since C++11 — calls arrive from many host threads)
-static bool use_umma() {
-  static const bool on = [] {
-    const char* e = getenv("B200TTS_CONV");
-    return !(e && strcmp(e, "simt") == 0);
+// ONE debug switch: B200TTS_DEBUG is a comma-separated list of flags (read once per process, thread-safe since C++11 —
+// calls arrive from many host threads).  Nothing here is needed in production; the defaults are the product path.
+//   simt          fp32 SIMT convs + SIMT attention everywhere (the in-library cross-check of the tensor-core path)
+//   attn_simt     SIMT attention only
+//   no_flow_chain flow decoder as one launch per conv instead of the persistent kernel (flow_chain.cuh)
+//   trace         per-conv %globaltimer phase trace on stderr (single-threaded use; implies no_flow_chain)
+static bool dbg_flag(const char* name) {
+  static const std::string flags = [] {
+    const char* e = getenv("B200TTS_DEBUG");
+    return std::string(",") + (e ? e : "") + ",";
   }();
-  return on;
+  return flags.find(std::string(",") + name + ",") != std::string::npos;
 }
-static bool res_from_planes() {
-  static const bool on = getenv("B200TTS_RES_FP32") == nullptr;
-  return on;
-}
-static bool mean_image() {
-  static const bool on = getenv("B200TTS_NO_MEAN_IMAGE") == nullptr;
-  return on;
-}
-// Round-2 work in progress (conv_chain.cuh): the flow decoder's convs in one cooperative launch.  Off by default.
-static bool flow_chain() {
-  static const bool on = getenv("B200TTS_FLOW_CHAIN") != nullptr;
+static bool use_umma() {
+  static const bool on = !dbg_flag("simt");
   return on;
 }
 static bool conv_trace() {
-  static const bool on = getenv("B200TTS_CONV_TRACE") != nullptr;
+  static const bool on = dbg_flag("trace");
+  return on;
+}
+static bool flow_chain_enabled() {
+  static const bool on = !dbg_flag("no_flow_chain") && !dbg_flag("trace") && !dbg_flag("simt");
   return on;
 }
 
@@ -418,6 +423,36 @@ static void glow_bind(b200tts_glow* m) {
     f.an_bias = W.get(s + ".an_bias", C);
     f.an_scale = W.get(s + ".an_scale", C);
   }
+  // flow blocks for the persistent decoder kernel, in execution order (FlowSpecDecoder runs reversed(flows), models.py:198)
+  bool chain_ok = m->n_blocks > 0 && C % 32 == 0 && Hd % 32 == 0;
+  for (const GlowFlow& f : m->flow) {
+    chain_ok = chain_ok && f.start.wu && f.end.wu && f.start.nsplit == 2 && f.end.nsplit == 2 && f.end.nt == m->flow[0].end.nt;
+    for (int l = 0; l < m->n_block_layers; ++l)
+      chain_ok = chain_ok && f.in[l].wu && f.rs[l].wu && f.in[l].nsplit == 2 && f.rs[l].nsplit == 2 &&
+                 f.in[l].nt == f.start.nt && f.rs[l].nt == f.start.nt;
+  }
+  if (chain_ok) chain_ok = flow_chain_geometry_ok(C / 2, Hd, m->kd, m->dil_rate, m->n_block_layers, m->flow[0].start.nt, m->flow[0].end.nt);
+  if (chain_ok) {
+    std::vector<FlowBlockDev> h(m->n_blocks);
+    for (int e = 0; e < m->n_blocks; ++e) {
+      const int blk = m->n_blocks - 1 - e;
+      const GlowFlow& f = m->flow[blk];
+      FlowBlockDev& d = h[e];
+      memset(&d, 0, sizeof(d));
+      int st = 0;
+      d.w[st] = f.start.wu; d.b[st++] = f.start.b;
+      for (int l = 0; l < m->n_block_layers; ++l) {
+        d.w[st] = f.in[l].wu; d.b[st++] = f.in[l].b;
+        d.w[st] = f.rs[l].wu; d.b[st++] = f.rs[l].b;
+      }
+      d.w[st] = f.end.wu; d.b[st++] = f.end.b;
+      d.inv = f.inv; d.an_bias = f.an_bias; d.an_scale = f.an_scale;
+      d.tap_index = blk;
+    }
+    B2_CUDA(cudaMalloc((void**)&m->flow_dev, sizeof(FlowBlockDev) * h.size()));
+    B2_CUDA(cudaMemcpy(m->flow_dev, h.data(), sizeof(FlowBlockDev) * h.size(), cudaMemcpyHostToDevice));
+    m->flow_nt_end = m->flow[0].end.nt;
+  }
 }
 
 static const int* lens_for_ln(const b200tts_call* c) { return c->xlen_d; }
@@ -443,7 +478,7 @@ static void glow_encode_impl(const b200tts_glow* m, b200tts_call* c, const int64
   if (um) need += 4 * Arena::pad(B * plane_item_bytes(H, prow, 3), 1) + Arena::pad(B * plane_item_bytes(F, prow, 3), 1) +
                   Arena::pad(B * plane_item_bytes(Fd, prow, 3), 1) + Arena::pad(B * plane_item_bytes(3 * H, prow, 3), 1);
   // tcgen05 attention needs the q/k/v image and handles up to 128 phonemes per item; longer batches use the SIMT kernel
-  const bool um_att = um && attn_umma_supported(H, m->n_heads, m->window, max_tx) && !getenv("B200TTS_ATTN_SIMT");
+  const bool um_att = um && attn_umma_supported(H, m->n_heads, m->window, max_tx) && !dbg_flag("attn_simt");
   c->enc.reserve(need + 4096);
   long long* ids_d = c->enc.take<long long>(B * max_tx);
   c->xlen_d = c->enc.take<int>(B);
@@ -607,9 +642,10 @@ static void glow_flow_impl(const b200tts_glow* m, b200tts_call* c, float noise_s
   if (um) need += Arena::pad(B * plane_item_bytes(C, prow, 2), 1) + 3 * Arena::pad(B * plane_item_bytes(Hd, prow, 2), 1);
   if (eps_host) need += Arena::pad((size_t)B * mel * eps_ld, 4);
   if (c->debug) need += Arena::pad((size_t)m->n_blocks * B * C * ldq, 4);
-  const bool chaining = flow_chain() && um && !c->debug && !conv_trace();
-  const size_t chain_cap = (size_t)m->n_blocks * (2 + 2 * m->n_block_layers);
-  if (chaining) need += Arena::pad(chain_cap * sizeof(ConvParams), 1) + Arena::pad(chain_cap, 4);
+  // the persistent kernel serves any batch (CTA groups walk the utterances) as long as one utterance's CTA group fits
+  const bool chain = um && m->flow_dev != nullptr && flow_chain_enabled() && Tq > 0 && flow_chain_fits(Tq);
+  const size_t n_counters = (size_t)B * m->n_blocks * (2 + 2 * m->n_block_layers);
+  if (chain) need += Arena::pad(n_counters, 4);
   c->dec.reserve(need + extra_bytes + 4096);
   c->idx_d = c->dec.take<int>(B * c->idx_ld);
   float* S = c->dec.take<float>((size_t)B * C * ldq);
@@ -648,19 +684,25 @@ static void glow_flow_impl(const b200tts_glow* m, b200tts_call* c, float noise_s
     p.lens = lens; p.len_mul = 1; p.Lin = Tq;
     return p;
   };
-  // chaining (B200TTS_FLOW_CHAIN=1): every conv after the first (which gathers fp32) is recorded and all of them run
-  // in one cooperative launch at the end
-  std::vector<ConvParams> chain;
-  auto run = [&](ConvParams& p, const ConvW& w) {
-    if (chaining && w.wu && p.xp) {
-      p.w = w.w; p.bias = w.b; p.Cin = w.cin; p.Cout = w.cout; p.K = w.k;
-      p.wu = w.wu; p.um_nt = w.nt; p.um_nsplit = w.nsplit;
-      chain.push_back(p);
-    } else {
-      B2_CHECK(chain.empty(), "flow chain: a layer without operand images in the middle of the chain");
-      conv(c, p, w, batch, Tq, s);
-    }
-  };
+  if (chain) {
+    // expand wrote the fp32 state; its operand image feeds the first `start` conv
+    launch_mean3_image(S, nullptr, nullptr, (long long)C * ldq, ldq, C, 1.f, 1.f, lens, 1, batch, S_p.ptr, S_p.bs, S_p.kc,
+                       S_p.rows, s);
+    c->launches++;
+    FlowChainParams fp;
+    memset(&fp, 0, sizeof(fp));
+    fp.blocks = m->flow_dev; fp.n_blocks = m->n_blocks; fp.n_wn = m->n_block_layers; fp.batch = batch;
+    fp.half = C / 2; fp.Hd = Hd; fp.K = m->kd; fp.dil_rate = m->dil_rate; fp.nt_end = m->flow_nt_end;
+    fp.lens = lens;
+    fp.S = S; fp.S_bs = (long long)C * ldq; fp.S_ld = ldq;
+    fp.taps = c->taps_d;
+    fp.S_p = (unsigned char*)S_p.ptr; fp.H_p = (unsigned char*)H_p.ptr; fp.A_p = (unsigned char*)A_p.ptr; fp.K_p = (unsigned char*)K_p.ptr;
+    fp.Sp_bs = S_p.bs; fp.Hp_bs = H_p.bs; fp.Sp_kc = S_p.kc; fp.Hp_kc = H_p.kc; fp.rows = prow;
+    fp.counter = c->dec.take<unsigned int>(n_counters);
+    c->launches += launch_flow_chain(fp, Tq, s);
+    return;
+  }
+  auto run = [&](ConvParams& p, const ConvW& w) { conv(c, p, w, batch, Tq, s); };
   for (int blk = m->n_blocks - 1; blk >= 0; --blk) {
     const GlowFlow& f = m->flow[blk];
     // CouplingBlock reverse                                     attentions.py:119-142
@@ -701,18 +743,6 @@ static void glow_flow_impl(const b200tts_glow* m, b200tts_call* c, float noise_s
     if (c->taps_d)
       B2_CUDA(cudaMemcpyAsync(c->taps_d + (size_t)blk * B * C * ldq, S, sizeof(float) * B * C * ldq,
                               cudaMemcpyDeviceToDevice, s));
-  }
-  if (!chain.empty()) {
-    const int n = (int)chain.size();
-    if (conv_chain_supported(chain.data(), n, batch, Tq)) {
-      B2_CHECK((size_t)n <= chain_cap, "flow chain longer than its workspace");
-      ConvParams* layers_d = reinterpret_cast<ConvParams*>(c->dec.take<unsigned char>(chain_cap * sizeof(ConvParams)));
-      unsigned int* counter_d = c->dec.take<unsigned int>(chain_cap);
-      B2_CUDA(cudaMemcpyAsync(layers_d, chain.data(), sizeof(ConvParams) * n, cudaMemcpyHostToDevice, s));
-      c->launches += launch_conv_chain(chain.data(), layers_d, n, counter_d, batch, Tq, s);
-    } else {  // too many CTAs for a cooperative launch (large batches): one launch per layer as usual
-      for (ConvParams& q : chain) c->launches += launch_conv_umma(q, batch, Tq, s);
-    }
   }
 }
 
@@ -905,7 +935,7 @@ static void hifigan_run(const b200tts_hifigan* m, b200tts_call* c, const float* 
           p.pix = u; p.pad_left = 1;  // one 3-tap conv, cout*u pixel-shuffled channels
           if (um && i == 0) {
             set_in(p, P_p);
-          } else if (um && prev_ump && in2 && in3 && mean_image()) {
+          } else if (um && prev_ump && in2 && in3) {
             // later stages read the MRF mean of three tensors: build its operand image once (into the previous stage's
             // dead U image) instead of letting each of the upsampler's n-tile CTAs gather and split it again
             launch_mean3_image(in1, in2, in3, (long long)cin * Lin_ld, Lin_ld, cin, in_div, 0.1f, frames_d, len_mul, batch,
@@ -959,7 +989,7 @@ static void hifigan_run(const b200tts_hifigan* m, b200tts_call* c, const float* 
         if (planes) {
           set_in(q, T_p[j]);
           if (d + 1 < r.ndil) set_out(q, R_p[j], 0.1f);
-          if (res_from_planes()) {
+          {
             // the block input already exists as a hi/lo image (c1's operand): read the residual from it and keep the
             // fp32 copy of x only where a non-MMA consumer needs it (last dilation: upsampler gather / conv_post)
             const Planes& rpl = d == 0 ? U_p : R_p[j];
@@ -975,29 +1005,7 @@ static void hifigan_run(const b200tts_hifigan* m, b200tts_call* c, const float* 
       };
       const bool umma_rb = m->resblock == 1 && use_umma() && nk == 3 && m->rb[i * nk].c1[0].wu != nullptr &&
                            !conv_trace();
-      // Large stages: run the branches one after the other (branch-major) so the live working set (U + one
-      // branch's R/T images) stays inside the 126 MB L2; small stages: one launch covers the three branches so the
-      // grid fills the GPU.
-      static const long long seq_min = [] {
-        const char* e = getenv("B200TTS_RB_SEQ_MIN");  // experiment knob; measured: no gain from branch-major order
-        return e ? atoll(e) : (1LL << 40);
-      }();
-      const long long tiles_per_branch = (long long)((L + 127) / 128) * batch * ((cout + 127) / 128);
-      const bool batched = umma_rb && tiles_per_branch < seq_min;
-      if (umma_rb && !batched) {
-        const int ndil = m->rb[i * nk].ndil;
-        for (int j = 0; j < 3; ++j)
-          for (int d = 0; d < ndil; ++d) {
-            ConvParams p1, p2;
-            bool pl;
-            fill_c1(j, d, p1, pl);
-            bind(p1, m->rb[i * nk + j].c1[d]);
-            c->launches += launch_conv_umma_batch(&p1, 1, batch, L, s);
-            fill_c2(j, d, p2, pl);
-            bind(p2, m->rb[i * nk + j].c2[d]);
-            c->launches += launch_conv_umma_batch(&p2, 1, batch, L, s);
-          }
-      } else if (batched) {
+      if (umma_rb) {
         const int ndil = m->rb[i * nk].ndil;
         for (int d = 0; d < ndil; ++d) {
           ConvParams ps[3];
@@ -1283,6 +1291,7 @@ int b200tts_call_create(int device, b200tts_call** out) {
   conv_umma_init_attributes();
   attention_init_attributes();
   attn_umma_init_attributes();
+  flow_chain_init_attributes();
   b200tts_call* c = new b200tts_call();
   c->device = device;
   B2_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));

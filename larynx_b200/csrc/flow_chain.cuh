@@ -1,0 +1,372 @@
+// flow_chain.cuh — the whole GlowTTS flow decoder (glow_tts/models.py:191-209: 12 x CouplingBlock reverse, each = start ->
+// 4 x (WN in_layer + gate -> res_skip) -> end + affine coupling + InvConvNear^-1 + ActNorm^-1) in ONE persistent launch.
+//
+// Why: at batch 1 the decoder is 120 dependent convs of 6-24 CTAs each; one launch per conv costs ~12 us of which ~7 us
+// are launch gap, TMEM allocation, barrier init and pipeline fill/drain (profiles/r1_tcgen05_summary.md), and the
+// res/skip epilogue paid two dependent global round trips for the fp32 hidden state and skip sum.
+//
+// Here a group of (time tiles x 6) CTAs owns one utterance for all layers of all blocks:
+//   * CTA (x, y) computes the 128-row time tile x of output-channel tile y of every layer that has such a tile;
+//   * layers are separated by a per-utterance barrier in global memory (one counter per layer: release = epilogue
+//     warps -> red.release.gpu, acquire = the activation-copy lane before it bulk-loads the next layer's A tiles); only the
+//     CTAs of ONE utterance synchronise, groups of different utterances never wait for each other;
+//   * the weight-copy lane does not wait for the barrier — weights are static — so the weights of layer l+1 stream into the
+//     ring while layer l is still in its epilogue;
+//   * the WN hidden state h and the skip sum never exist in fp32 memory: CTAs y = 0..2 keep their 64 channels of h, CTAs
+//     y = 3..5 their 64 channels of the skip sum, as a PERSISTENT TMEM accumulator — `start` writes it, every res_skip
+//     conv accumulates onto it with the MMA itself (h += rs[:, :192], skip += rs[:, 192:], glow_tts/layers.py:151-160) and
+//     the epilogue only reads it to emit the bf16 operand image of the new h (the next in_layer's A operand);
+//   * barriers, TMEM (256 columns: working + persistent accumulator) and the operand rings are set up once per launch.
+// The conv itself is the plane-mode path of conv_umma_kernel<1, 2, ...>: same operand images, same MMA sequence per
+// k-chunk, the very same epilogue text (conv_umma_epilogue.inc) for the gate and the coupling.
+#pragma once
+#include "conv_umma.cuh"
+#include "flow_chain_params.cuh"
+
+namespace b2 {
+
+constexpr int FC_NT = 64;      // N tile of start / in / res_skip (pack.py: B200TTS_GLOW_NT)
+constexpr int FC_YT = 6;       // channel-tile CTAs per time tile = 2 * Hd / FC_NT
+constexpr int FC_EW = 8;       // epilogue warps
+constexpr int FC_G = 5;        // taps per weight slot (one bulk copy per 32-channel chunk of an in_layer)
+constexpr int FC_WST = 3, FC_AST = 4;
+constexpr int FC_HALO = 16;    // max (K-1)*dil
+constexpr int FC_RA = 128 + FC_HALO;
+constexpr int FC_THREADS = FC_EW * 32 + 96;
+constexpr uint32_t FC_A_SPLIT = UM_KCH * FC_RA * 16;
+constexpr uint32_t FC_A_STAGE = 2 * FC_A_SPLIT;
+constexpr uint32_t FC_W_SLOT = (uint32_t)FC_G * 2 * UM_KCH * FC_NT * 16;
+constexpr size_t FC_SMEM = (size_t)FC_AST * FC_A_STAGE + (size_t)FC_WST * FC_W_SLOT + 512 + sizeof(ConvParams) + 16 +
+                           4 * (64 + 64 + 16 + 2 * 256);
+
+enum FlowStepKind { FS_START = 0, FS_IN = 1, FS_RS = 2, FS_RS_LAST = 3, FS_END = 4 };
+
+// what CTA row y does in one step of a coupling block
+struct FlowStep {
+  int kind, l;
+  bool active;     // this CTA has a tile in this step
+  int wt;          // weight n-tile it multiplies with
+  int NT, nch, K, dil, pad;
+  int acc;         // 0: working accumulator (TMEM columns [0, 128)), 1: persistent accumulator ([128, 256))
+  int init;        // 1: the first MMA overwrites the accumulator, 0: accumulates onto it
+  int epi;         // -1: no epilogue (the persistent skip sum just grows), else EpiMode
+  int n_active;    // CTA rows taking part (for the barrier count)
+};
+
+__device__ __forceinline__ FlowStep flow_step(const FlowChainParams& fp, int step, int y) {
+  FlowStep s;
+  const int last = 1 + 2 * fp.n_wn;
+  s.l = step > 0 ? (step - 1) >> 1 : 0;
+  s.NT = FC_NT; s.K = 1; s.dil = 1; s.pad = 0; s.acc = 0; s.init = 1; s.epi = EPI_PLAIN; s.wt = y;
+  s.nch = (fp.Hd + UM_BKC - 1) / UM_BKC;
+  const int hd_tiles = fp.Hd / FC_NT;
+  if (step == 0) {
+    s.kind = FS_START;
+    s.nch = (fp.half + UM_BKC - 1) / UM_BKC;
+    s.n_active = hd_tiles;
+    s.active = y < hd_tiles;
+    s.acc = 1;
+  } else if (step == last) {
+    s.kind = FS_END;
+    s.NT = fp.nt_end;
+    s.n_active = (2 * fp.half + fp.nt_end - 1) / fp.nt_end;
+    s.active = y < s.n_active;
+    s.epi = EPI_COUPLING;
+  } else if ((step - 1) & 1) {
+    const bool is_last = s.l == fp.n_wn - 1;
+    s.kind = is_last ? FS_RS_LAST : FS_RS;
+    s.acc = 1;
+    if (!is_last) {
+      s.n_active = 2 * hd_tiles;
+      s.active = true;
+      const bool skip = y >= hd_tiles;
+      s.init = skip && s.l == 0;
+      s.epi = skip ? -1 : EPI_PLAIN;
+    } else {  // Cout = Hd, all of it skip: the skip owners (y >= hd_tiles) take weight tile y - hd_tiles
+      s.n_active = hd_tiles;
+      s.active = y >= hd_tiles;
+      s.wt = y - hd_tiles;
+      s.init = s.l == 0;
+    }
+  } else {
+    s.kind = FS_IN;
+    s.K = fp.K;
+    int d = 1;
+    for (int j = 0; j < s.l; ++j) d *= fp.dil_rate;
+    s.dil = d;
+    s.pad = (fp.K * d - d) / 2;
+    s.n_active = 2 * hd_tiles;
+    s.active = true;
+    s.epi = EPI_GATE;
+  }
+  return s;
+}
+
+__device__ __forceinline__ unsigned int fc_ld_acquire(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fc_red_release(unsigned int* p) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+}
+__device__ __forceinline__ void fc_epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(FC_EW * 32) : "memory"); }
+
+__global__ void __launch_bounds__(FC_THREADS, 1) flow_chain_kernel(const __grid_constant__ FlowChainParams fp) {
+  using namespace umma;
+  constexpr int MT = 1, NSPLIT = 2, NACC = 2, EW = FC_EW;
+  constexpr int RA = FC_RA;
+  constexpr int W_MMA = EW, W_LOAD = EW + 1, W_ALOAD = EW + 2;
+  constexpr uint32_t a_split_bytes = FC_A_SPLIT, a_stage = FC_A_STAGE, w_slot = FC_W_SLOT;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* sA = smem_raw;
+  unsigned char* sW = smem_raw + FC_AST * a_stage;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + FC_WST * w_slot);
+  uint64_t* a_full = bars;          // [AST]
+  uint64_t* a_empty = bars + 4;     // [AST]
+  uint64_t* w_full = bars + 8;      // [WST]
+  uint64_t* w_empty = bars + 12;    // [WST]
+  uint64_t* acc_full = bars + 16;   // MMA -> epilogue
+  uint64_t* acc_empty = bars + 17;  // epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  ConvParams* s_p = reinterpret_cast<ConvParams*>(bars + 64);  // epilogue parameters of the current step (conv_umma_epilogue.inc)
+  float* s_wbias = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(s_p) + ((sizeof(ConvParams) + 15) & ~(size_t)15));
+  float* s_pbias = s_wbias + 64;    // running bias of the persistent accumulator (sum of the biases accumulated so far)
+  float* s_inv = s_pbias + 64;
+  float* s_anb = s_inv + 16;
+  float* s_ans = s_anb + 256;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int mtile = blockIdx.x, y = blockIdx.y;
+  const int t0 = mtile * 128;
+  constexpr uint32_t tmem_cols = 256;
+  const int n_steps = 2 + 2 * fp.n_wn;
+
+  if (tid == 0) {
+    for (int i = 0; i < FC_AST; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < FC_WST; ++i) {
+      mbar_init(&w_full[i], 1);
+      mbar_init(&w_empty[i], 1);
+    }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, EW);
+    fence_barrier_init();
+  }
+  if (warp == W_MMA) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == W_LOAD) {
+    // ===================== weight producer: runs ahead of the layer barriers (weights are static) =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 1;
+      for (int b = blockIdx.z; b < fp.batch; b += gridDim.z) {
+        if (t0 >= fp.lens[b]) continue;
+        for (int blk = 0; blk < fp.n_blocks; ++blk) {
+          const FlowBlockDev& fb = fp.blocks[blk];
+          for (int step = 0; step < n_steps; ++step) {
+            const FlowStep st = flow_step(fp, step, y);
+            if (!st.active) continue;
+            const uint32_t w_stage = (uint32_t)NSPLIT * UM_KCH * st.NT * 16;
+            const unsigned char* gw = reinterpret_cast<const unsigned char*>(fb.w[step]) + (size_t)st.wt * st.nch * st.K * w_stage;
+            for (int c = 0; c < st.nch; ++c)
+              for (int k0 = 0; k0 < st.K; k0 += FC_G) {
+                const uint32_t bytes = (uint32_t)min(FC_G, st.K - k0) * w_stage;
+                mbar_wait(&w_empty[s], ph);
+                mbar_arrive_expect_tx(&w_full[s], bytes);
+                bulk_g2s(sW + (size_t)s * w_slot, gw + ((size_t)c * st.K + k0) * w_stage, bytes, &w_full[s]);
+                if (++s == FC_WST) { s = 0; ph ^= 1; }
+              }
+          }
+        }
+      }
+    }
+  } else if (warp == W_ALOAD) {
+    // ===================== activation producer: waits for the previous layer of THIS utterance, then bulk-copies ========
+    if (lane == 0) {
+      int as = 0;
+      uint32_t aph = 1;
+      for (int b = blockIdx.z; b < fp.batch; b += gridDim.z) {
+        const int Lb = fp.lens[b];
+        if (t0 >= Lb) continue;
+        const unsigned int m_tiles = (unsigned int)((Lb + 127) / 128);
+        const unsigned int* cnt = fp.counter + (size_t)b * fp.n_blocks * n_steps;
+        unsigned int prev_expect = 0;
+        for (int blk = 0; blk < fp.n_blocks; ++blk) {
+          for (int step = 0; step < n_steps; ++step) {
+            const FlowStep st = flow_step(fp, step, y);
+            const int L = blk * n_steps + step;
+            if (st.active) {
+              if (L > 0) {
+                // every CTA of this utterance has finished (and published) layer L-1 — and with it, in order, all earlier ones
+                unsigned int spins = 0;
+                while (fc_ld_acquire(cnt + (L - 1)) < prev_expect) {
+                  __nanosleep(20);
+                  if (++spins > (1u << 24)) {  // seconds: a lost arrival must fail loudly, not hang the device
+                    printf("flow_chain: barrier %d of item %d timed out (CTA %d,%d,%d)\n", L - 1, b, blockIdx.x, blockIdx.y, blockIdx.z);
+                    __trap();
+                  }
+                }
+                asm volatile("fence.proxy.async;" ::: "memory");  // other CTAs' generic-proxy writes -> our async-proxy reads
+              }
+              const unsigned char* img;
+              long long bs;
+              int kc_total;
+              if (st.kind == FS_START) { img = fp.S_p; bs = fp.Sp_bs; kc_total = fp.Sp_kc; }
+              else if (st.kind == FS_IN) { img = fp.H_p; bs = fp.Hp_bs; kc_total = fp.Hp_kc; }
+              else if (st.kind == FS_END) { img = fp.K_p; bs = fp.Hp_bs; kc_total = fp.Hp_kc; }
+              else { img = fp.A_p; bs = fp.Hp_bs; kc_total = fp.Hp_kc; }
+              const unsigned char* xp = img + (size_t)b * bs;
+              const uint32_t kc_bytes = (uint32_t)(128 + (st.K - 1) * st.dil) * 16;
+              const long long row0 = (long long)t0 - st.pad + UM_PADL;
+              for (int c = 0; c < st.nch; ++c, as = (as + 1 == FC_AST ? 0 : as + 1), aph ^= (as == 0)) {
+                mbar_wait(&a_empty[as], aph);
+                mbar_arrive_expect_tx(&a_full[as], NSPLIT * UM_KCH * kc_bytes);
+                unsigned char* dst = sA + (size_t)as * a_stage;
+                for (int sp = 0; sp < NSPLIT; ++sp)
+#pragma unroll
+                  for (int kc = 0; kc < UM_KCH; ++kc)
+                    bulk_g2s(dst + sp * a_split_bytes + kc * RA * 16,
+                             xp + (((size_t)sp * kc_total + c * UM_KCH + kc) * fp.rows + row0) * 16, kc_bytes, &a_full[as]);
+              }
+            }
+            prev_expect = (unsigned int)st.n_active * m_tiles;
+          }
+        }
+      }
+    }
+  } else if (warp == W_MMA) {
+    // ===================== MMA issuer (same sequence per k-chunk as conv_umma_kernel, NSPLIT = 2) =====================
+    int ws = 0, as = 0;
+    uint32_t wph = 0, aph = 0, use = 0;
+    const uint64_t a_desc0 = make_smem_desc(smem_u32(sA), RA * 16, 128);
+    const uint32_t a_ks = (2 * RA * 16) >> 4, a_sp = a_split_bytes >> 4;
+    for (int b = blockIdx.z; b < fp.batch; b += gridDim.z) {
+      if (t0 >= fp.lens[b]) continue;
+      for (int blk = 0; blk < fp.n_blocks; ++blk)
+        for (int step = 0; step < n_steps; ++step) {
+          const FlowStep st = flow_step(fp, step, y);
+          if (!st.active) continue;  // uniform across the warp
+          const int NT = st.NT, K = st.K, dil = st.dil, nch = st.nch;
+          const uint32_t w_stage = (uint32_t)NSPLIT * UM_KCH * NT * 16;
+          const uint32_t idesc1 = make_idesc_bf16_f32(128, NT), idesc2 = make_idesc_bf16_f32(128, 2 * NT);
+          const uint64_t b_desc0 = make_smem_desc(smem_u32(sW), NSPLIT * NT * 16, 128);
+          const uint32_t b_ks = (2 * NSPLIT * NT * 16) >> 4;
+          const uint32_t tm = tmem + (st.acc ? 128u : 0u);
+          mbar_wait(acc_empty, (use & 1) ^ 1);  // the epilogue of this CTA's previous step is done with the accumulators
+          tc_fence_after();
+          for (int c = 0; c < nch; ++c) {
+            mbar_wait(&a_full[as], aph);
+            tc_fence_after();
+            const uint64_t a_c = a_desc0 + ((as * a_stage) >> 4);
+            for (int k0 = 0; k0 < K; k0 += FC_G) {
+              mbar_wait(&w_full[ws], wph);
+              tc_fence_after();
+              const int cnt = min(FC_G, K - k0);
+              if (elect_one()) {
+                for (int kk = 0; kk < cnt; ++kk) {
+                  const int k = k0 + kk;
+                  const uint64_t a_k = a_c + (uint32_t)(k * dil);
+                  const uint64_t b_k = b_desc0 + ((ws * w_slot + kk * w_stage) >> 4);
+                  const uint32_t first = (c == 0 && k == 0 && st.init) ? 0u : 1u;
+#pragma unroll
+                  for (int ks = 0; ks < UM_BKC / 16; ++ks) {
+                    const uint64_t a0 = a_k + ks * a_ks, b0 = b_k + ks * b_ks;
+                    const uint32_t acc0 = ks == 0 ? first : 1u;
+                    mma_bf16_ss(tm, a0, b0, idesc2, acc0);            // hi x [hi|lo] -> [c0|c1]
+                    mma_bf16_ss(tm + NT, a0 + a_sp, b0, idesc1, 1u);  // lo x hi      -> c1
+                  }
+                }
+                mma_commit(&w_empty[ws]);
+              }
+              __syncwarp();
+              if (++ws == FC_WST) { ws = 0; wph ^= 1; }
+            }
+            if (elect_one()) mma_commit(&a_empty[as]);
+            __syncwarp();
+            if (++as == FC_AST) { as = 0; aph ^= 1; }
+          }
+          if (elect_one()) mma_commit(acc_full);
+          __syncwarp();
+          ++use;
+        }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    uint32_t use = 0;
+    const int it = 1;  // (tracing in the shared epilogue text is tied to it == 0: off)
+    const ConvParams& p = *s_p;
+    for (int b = blockIdx.z; b < fp.batch; b += gridDim.z) {
+      const int Lb = fp.lens[b];
+      if (t0 >= Lb) continue;
+      unsigned int* cnt = fp.counter + (size_t)b * fp.n_blocks * n_steps;
+      for (int blk = 0; blk < fp.n_blocks; ++blk) {
+        const FlowBlockDev& fb = fp.blocks[blk];
+        for (int step = 0; step < n_steps; ++step) {
+          const FlowStep st = flow_step(fp, step, y);
+          if (!st.active) continue;
+          const int NT = st.NT;
+          const int n0 = st.wt * NT;  // first packed output channel of this CTA's tile
+          // ---- this step's epilogue constants -> smem (the previous step's readers are past fc_epi_bar below)
+          const float* bias = fb.b[step];
+          if (st.acc == 0) {
+            for (int i = tid; i < NT; i += EW * 32) s_wbias[i] = bias[n0 + i];
+          } else if (tid < NT) {  // persistent accumulator: its bias is the sum of the biases of everything accumulated
+            s_pbias[tid] = st.init ? bias[n0 + tid] : s_pbias[tid] + bias[n0 + tid];
+          }
+          if (st.kind == FS_END) {
+            if (tid < 16) s_inv[tid] = fb.inv[tid];
+            for (int i = tid; i < 2 * fp.half; i += EW * 32) {
+              s_anb[i] = fb.an_bias[i];
+              s_ans[i] = fb.an_scale[i];
+            }
+          }
+          if (tid == 0 && st.epi >= 0) {
+            ConvParams q;
+            q.epi = st.epi;
+            q.Cout = st.kind == FS_END ? 2 * fp.half : (st.kind == FS_IN ? 2 * fp.Hd : fp.Hd);
+            q.half = fp.half;
+            if (st.kind == FS_END) {
+              q.y = fp.S; q.y_bs = fp.S_bs; q.y_ld = fp.S_ld;
+              q.yp = fp.S_p; q.yp_bs = fp.Sp_bs; q.yp_kc = fp.Sp_kc;
+              if (fp.taps) q.tap = fp.taps + (size_t)fb.tap_index * fp.batch * fp.S_bs;
+            } else {
+              q.yp = st.kind == FS_IN ? fp.A_p : (st.kind == FS_RS_LAST ? fp.K_p : fp.H_p);
+              q.yp_bs = fp.Hp_bs; q.yp_kc = fp.Hp_kc;
+            }
+            q.yp_rows = fp.rows; q.yp_nsplit = 2; q.yp_slope = 1.f;
+            *s_p = q;
+          }
+          fc_epi_bar();
+          mbar_wait(acc_full, use & 1);
+          tc_fence_after();
+          if (st.epi >= 0) {
+            const uint32_t tm = tmem + (st.acc ? 128u : 0u);
+            const float* s_bias = st.acc ? s_pbias : s_wbias;
+#include "conv_umma_epilogue.inc"
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty);
+          ++use;
+          // publish this CTA's part of the layer: all epilogue warps' global writes, then ONE release increment
+          __threadfence();
+          asm volatile("fence.proxy.async;" ::: "memory");
+          fc_epi_bar();
+          if (tid == 0) fc_red_release(cnt + (blk * n_steps + step));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == W_MMA) tmem_dealloc(tmem, tmem_cols);
+}
+
+}  // namespace b2

@@ -61,10 +61,11 @@ void launch_mean3_image(const float* x1, const float* x2, const float* x3, long 
                         const int* lens, int len_mul, int batch, void* img, long long img_bs, int kc_total, int rows,
                         cudaStream_t s);
 
-// chained convs in one cooperative launch (conv_chain.cu; round-2 work in progress, off unless B200TTS_FLOW_CHAIN=1)
-void conv_chain_init_attributes();
-bool conv_chain_supported(const ConvParams* layers, int n_layers, int batch, int Lmax);
-int launch_conv_chain(const ConvParams* layers, const ConvParams* layers_d, int n_layers, unsigned int* counter_d, int batch,
-                      int Lmax, cudaStream_t s);
+// the whole flow decoder in one persistent cooperative launch (flow_chain.cu)
+struct FlowChainParams;
+void flow_chain_init_attributes();
+bool flow_chain_geometry_ok(int half, int Hd, int K, int dil_rate, int n_wn, int nt_hidden, int nt_end);
+bool flow_chain_fits(int Lmax);
+int launch_flow_chain(const FlowChainParams& fp, int Lmax, cudaStream_t s);
 
 }  // namespace b2

@@ -17,7 +17,6 @@ This blob is also the unit that is broadcast once over NCCL when several GPUs se
 """
 from __future__ import annotations
 
-import os
 import struct
 from typing import Optional, Dict, List, Tuple
 
@@ -223,7 +222,7 @@ def pack_glow(sd: Dict[str, np.ndarray], config: dict) -> np.ndarray:
            m["n_block_layers"], m["n_sqz"], m["n_split"], Hd]
     bw = BlobWriter(KIND_GLOW, cfg)
 
-    bw.nt_max = int(os.environ.get("B200TTS_GLOW_NT", "64"))  # GlowTTS runs on 1-4 time tiles: favour more N tiles
+    bw.nt_max = 64  # GlowTTS runs on 1-4 time tiles: favour more N tiles (flow_chain.cuh is built for this tile)
     g = lambda k: _np(sd[k])
     bw.add("emb", g("encoder.emb.weight"))
     for i in range(3):
@@ -301,9 +300,7 @@ def pack_hifigan(sd: Dict[str, np.ndarray], config: dict) -> np.ndarray:
             cfg[28 + j * 3 + d] = dv
     bw = BlobWriter(KIND_HIFIGAN, cfg)
     g = lambda k: _np(sd[k])
-    # ResBlock output-channel tile (experiment knob): 64-wide tiles halve the weight bytes per output at twice the
-    # activation bytes; measured equal within 1 % on B200, so the wider tile (fewer CTAs) stays the default
-    rb_nt = int(os.environ.get("B200TTS_VOC_NT", "128"))
+    rb_nt = 128  # ResBlock output-channel tile (64-wide tiles measured equal within 1 % on B200: fewer CTAs win)
     bw.add_conv("conv_pre", fold_weight_norm(sd, "conv_pre"), g("conv_pre.bias"))
     for i, (u, k) in enumerate(zip(rates, ks)):
         wt = fold_weight_norm(sd, f"ups.{i}")

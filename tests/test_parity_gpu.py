@@ -318,7 +318,7 @@ def test_reentrant_from_host_threads():
 
 
 def test_simt_reference_path_still_matches():
-    """The fp32 SIMT conv path (B200TTS_CONV=simt) is kept as an in-library cross-check of the tensor-core path."""
+    """The fp32 SIMT conv path (B200TTS_DEBUG=simt) is kept as an in-library cross-check of the tensor-core path."""
     import subprocess
     import sys
 
@@ -337,7 +337,7 @@ def test_simt_reference_path_still_matches():
     outs = {}
     for mode in ("simt", "umma"):
         f = os.path.join(tempfile.mkdtemp(), mode + ".npz")
-        env = dict(os.environ, B200TTS_CONV=mode)
+        env = dict(os.environ, B200TTS_DEBUG="simt" if mode == "simt" else "")
         subprocess.run([sys.executable, "-c", code, f], check=True, env=env, cwd=os.path.dirname(os.path.dirname(__file__)))
         outs[mode] = np.load(f)
     assert outs["simt"]["mel"].shape == outs["umma"]["mel"].shape

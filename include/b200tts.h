@@ -98,6 +98,10 @@ int b200tts_glow_alignment(const b200tts_glow* m, b200tts_call* call, float* log
  * b200tts_call_set_debug(call,1) was set before decode). out [batch][2*mel][ld] */
 int b200tts_call_set_debug(b200tts_call* call, int on);
 int b200tts_glow_flow_tap(const b200tts_glow* m, b200tts_call* call, int blk, float* out, int ld);
+/* The production noise stream on its own (no reference counterpart: glow_tts/models.py:348 draws torch.randn_like):
+ * out [batch][mel][ld] (host or device), element (b, c, f) = the N(0,1) draw that decode with eps == NULL and this seed
+ * adds to frame f of channel c of item b.  Exists so that the generator's moments can be tested. */
+int b200tts_debug_noise(b200tts_call* call, uint64_t seed, int batch, int mel, int n, float* out, int ld);
 
 /* ---- HiFi-GAN (hifi_gan/models.py:186-202 Generator.forward) ------------------------------ */
 int b200tts_hifigan_create(const void* blob, size_t nbytes, int device, b200tts_hifigan** out);

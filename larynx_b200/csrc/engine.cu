@@ -462,13 +462,16 @@ static void glow_encode_impl(const b200tts_glow* m, b200tts_call* c, const int64
   B2_CHECK(batch > 0 && max_tx > 0, "empty batch");
   B2_CHECK(m->W.device == c->device, "model and call live on different devices");
   B2_CUDA(cudaSetDevice(c->device));
+  // the state of an earlier encode dies here: a failed encode must not leave decode / tts_finish a half-written one
+  c->enc_model = nullptr;
+  c->idx_d = nullptr;
   cudaStream_t s = c->stream;
   const int H = m->H, F = m->F, Fd = m->Fd, mel = m->mel;
   const int ld = round_up(max_tx, 32);
   const long long B = batch;
   // ---- workspace
   size_t need = 0;
-  need += Arena::pad(B * max_tx, 8) + 3 * Arena::pad(B, 4) + 2 * Arena::pad(B * max_tx, 4) + Arena::pad(B * max_tx, 4);
+  need += Arena::pad(B * max_tx, 8) + 4 * Arena::pad(B, 4) + 2 * Arena::pad(B * max_tx, 4) + Arena::pad(B * max_tx, 4);
   const size_t act = (size_t)B * ld;
   need += Arena::pad(act * H, 4) * 4 + Arena::pad(act * 3 * H, 4) + Arena::pad(act * F, 4) +
           Arena::pad(act * Fd, 4) * 2 + Arena::pad(act * mel, 4);
@@ -484,6 +487,7 @@ static void glow_encode_impl(const b200tts_glow* m, b200tts_call* c, const int64
   c->xlen_d = c->enc.take<int>(B);
   c->ylen_d = c->enc.take<int>(B);
   c->sqlen_d = c->enc.take<int>(B);
+  int* bad_id_d = c->enc.take<int>(1);
   c->wceil_d = c->enc.take<int>(B * max_tx);
   c->cum_d = c->enc.take<int>(B * max_tx);
   c->logw_d = c->enc.take<float>(B * max_tx);
@@ -526,7 +530,8 @@ static void glow_encode_impl(const b200tts_glow* m, b200tts_call* c, const int64
     return p;
   };
   // embedding * sqrt(H)                                         models.py:119-121
-  launch_embed(ids_d, lens, batch, max_tx, m->emb, m->V, H, X, (long long)H * ld, ld, s);
+  B2_CUDA(cudaMemsetAsync(bad_id_d, 0, sizeof(int), s));
+  launch_embed(ids_d, lens, batch, max_tx, m->emb, m->V, H, X, (long long)H * ld, ld, bad_id_d, s);
   c->launches++;
   // prenet: 3 x (conv k5 -> LN -> ReLU), 1x1 proj + residual   layers.py:73-80
   {
@@ -609,7 +614,10 @@ static void glow_encode_impl(const b200tts_glow* m, b200tts_call* c, const int64
   }
   c->y_len_h.resize(batch);
   B2_CUDA(cudaMemcpyAsync(c->y_len_h.data(), c->ylen_d, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
+  int bad_id = 0;
+  B2_CUDA(cudaMemcpyAsync(&bad_id, bad_id_d, sizeof(int), cudaMemcpyDeviceToHost, s));
   tm.stop_and_sync();
+  B2_CHECK(bad_id == 0, "phoneme id out of range for this voice (0 <= id < num_symbols)");
   c->enc_model = m;
   c->batch = batch;
   c->max_tx = max_tx;
@@ -619,7 +627,6 @@ static void glow_encode_impl(const b200tts_glow* m, b200tts_call* c, const int64
     c->ty_max = std::max(c->ty_max, c->y_len_h[b]);
     if (y_len_out) y_len_out[b] = c->y_len_h[b];
   }
-  c->idx_d = nullptr;
 }
 
 // Runs expand+noise+flow on c->stream.  Leaves the un-squeezed result in the squeezed state buffer
@@ -699,6 +706,35 @@ static void glow_flow_impl(const b200tts_glow* m, b200tts_call* c, float noise_s
     fp.S_p = (unsigned char*)S_p.ptr; fp.H_p = (unsigned char*)H_p.ptr; fp.A_p = (unsigned char*)A_p.ptr; fp.K_p = (unsigned char*)K_p.ptr;
     fp.Sp_bs = S_p.bs; fp.Hp_bs = H_p.bs; fp.Sp_kc = S_p.kc; fp.Hp_kc = H_p.kc; fp.rows = prow;
     fp.counter = c->dec.take<unsigned int>(n_counters);
+    static const bool trace = dbg_flag("chain_trace");  // debug: per-layer phase stamps of utterance 0, time tile 0
+    const int n_layers = m->n_blocks * (2 + 2 * m->n_block_layers);
+    if (trace) {
+      static unsigned long long* tr = nullptr;
+      if (!tr) B2_CUDA(cudaMallocManaged(&tr, sizeof(unsigned long long) * 8 * 6 * 256));
+      B2_CUDA(cudaDeviceSynchronize());
+      memset(tr, 0, sizeof(unsigned long long) * 8 * 6 * 256);
+      fp.trace = tr;
+      c->launches += launch_flow_chain(fp, Tq, s);
+      B2_CUDA(cudaDeviceSynchronize());
+      const int n_steps = 2 + 2 * m->n_block_layers;
+      const unsigned long long t_start = tr[0] ? tr[0] : tr[1];
+      for (int L = 0; L < n_layers && L < 2 * n_steps; ++L) {  // first two blocks
+        fprintf(stderr, "[chain] L%3d step %d:", L, L % n_steps);
+        for (int y = 0; y < 6; ++y) {
+          const unsigned long long* e = tr + ((size_t)L * 6 + y) * 8;
+          if (!e[4]) { fprintf(stderr, " | y%d idle", y); continue; }
+          fprintf(stderr, " | y%d bar %6.2f A %5.2f W %5.2f mma %5.2f acc %5.2f epi %5.2f pub %5.2f", y, (e[0] - t_start) * 1e-3,
+                  (e[1] - e[0]) * 1e-3, (e[2] > e[1] ? e[2] - e[1] : 0) * 1e-3, (e[3] - e[2]) * 1e-3, (e[4] - e[3]) * 1e-3, (e[5] - e[4]) * 1e-3,
+                  (e[6] - e[5]) * 1e-3);
+        }
+        fprintf(stderr, "\n");
+      }
+      unsigned long long t_end = 0;
+      for (int i = 0; i < 8 * 6 * n_layers; ++i) t_end = std::max(t_end, tr[i]);
+      fprintf(stderr, "[chain] %d layers, %.1f us from first barrier to last publish (%.2f us per layer)\n", n_layers,
+              (t_end - t_start) * 1e-3, (t_end - t_start) * 1e-3 / n_layers);
+      return;
+    }
     c->launches += launch_flow_chain(fp, Tq, s);
     return;
   }
@@ -1408,6 +1444,24 @@ int b200tts_glow_alignment(const b200tts_glow* m, b200tts_call* c, float* logw, 
     copy_out_2d(idx, idx_ld, c->idx_d, c->idx_ld, c->batch, std::min(idx_ld, c->idx_ld), sizeof(int), s);
   }
   B2_CUDA(cudaStreamSynchronize(s));
+  B2_API_END
+}
+
+int b200tts_debug_noise(b200tts_call* c, uint64_t seed, int batch, int mel, int n, float* out, int ld) {
+  B2_API_BEGIN
+  B2_CHECK(c && out, "null argument");
+  B2_CHECK(batch > 0 && mel > 0 && n >= 0 && ld >= n, "bad noise shape");
+  B2_CUDA(cudaSetDevice(c->device));
+  const bool dev = is_device_ptr(out);
+  float* d = out;
+  if (!dev) {
+    c->stg.reserve(Arena::pad((size_t)batch * mel * ld, 4) + 4096);
+    d = c->stg.take<float>((size_t)batch * mel * ld);
+  }
+  launch_noise_fill(seed, batch, mel, n, d, (long long)mel * ld, ld, c->stream);
+  c->launches++;
+  if (!dev) B2_CUDA(cudaMemcpyAsync(out, d, sizeof(float) * batch * mel * ld, cudaMemcpyDeviceToHost, c->stream));
+  B2_CUDA(cudaStreamSynchronize(c->stream));
   B2_API_END
 }
 

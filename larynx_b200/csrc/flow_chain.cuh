@@ -112,6 +112,11 @@ __device__ __forceinline__ void fc_red_release(unsigned int* p) {
 }
 __device__ __forceinline__ void fc_epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(FC_EW * 32) : "memory"); }
 
+#define FC_TRACE(L, ev)                                                                              \
+  do {                                                                                               \
+    if (fp.trace && blockIdx.x == 0 && blockIdx.z == 0 && b == 0) fp.trace[((size_t)(L)*FC_YT + y) * 8 + (ev)] = gtimer(); \
+  } while (0)
+
 __global__ void __launch_bounds__(FC_THREADS, 1) flow_chain_kernel(const __grid_constant__ FlowChainParams fp) {
   using namespace umma;
   constexpr int MT = 1, NSPLIT = 2, NACC = 2, EW = FC_EW;
@@ -215,6 +220,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) flow_chain_kernel(const __grid_
                 }
                 asm volatile("fence.proxy.async;" ::: "memory");  // other CTAs' generic-proxy writes -> our async-proxy reads
               }
+              FC_TRACE(L, 0);
               const unsigned char* img;
               long long bs;
               int kc_total;
@@ -264,10 +270,12 @@ __global__ void __launch_bounds__(FC_THREADS, 1) flow_chain_kernel(const __grid_
           for (int c = 0; c < nch; ++c) {
             mbar_wait(&a_full[as], aph);
             tc_fence_after();
+            if (c == 0 && lane == 0) FC_TRACE(blk * n_steps + step, 1);
             const uint64_t a_c = a_desc0 + ((as * a_stage) >> 4);
             for (int k0 = 0; k0 < K; k0 += FC_G) {
               mbar_wait(&w_full[ws], wph);
               tc_fence_after();
+              if (c == 0 && k0 == 0 && lane == 0) FC_TRACE(blk * n_steps + step, 2);
               const int cnt = min(FC_G, K - k0);
               if (elect_one()) {
                 for (int kk = 0; kk < cnt; ++kk) {
@@ -294,6 +302,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) flow_chain_kernel(const __grid_
           }
           if (elect_one()) mma_commit(acc_full);
           __syncwarp();
+          if (lane == 0) FC_TRACE(blk * n_steps + step, 3);
           ++use;
         }
     }
@@ -346,6 +355,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) flow_chain_kernel(const __grid_
           fc_epi_bar();
           mbar_wait(acc_full, use & 1);
           tc_fence_after();
+          if (tid == 0) FC_TRACE(blk * n_steps + step, 4);
           if (st.epi >= 0) {
             const uint32_t tm = tmem + (st.acc ? 128u : 0u);
             const float* s_bias = st.acc ? s_pbias : s_wbias;
@@ -355,11 +365,13 @@ __global__ void __launch_bounds__(FC_THREADS, 1) flow_chain_kernel(const __grid_
           __syncwarp();
           if (lane == 0) mbar_arrive(acc_empty);
           ++use;
+          if (tid == 0) FC_TRACE(blk * n_steps + step, 5);
           // publish this CTA's part of the layer: all epilogue warps' global writes, then ONE release increment
           __threadfence();
           asm volatile("fence.proxy.async;" ::: "memory");
           fc_epi_bar();
           if (tid == 0) fc_red_release(cnt + (blk * n_steps + step));
+          if (tid == 0) FC_TRACE(blk * n_steps + step, 6);
         }
       }
     }

@@ -32,6 +32,7 @@ struct FlowChainParams {
   long long Sp_bs, Hp_bs;      // bytes per batch item (S_p | the three Hd-channel images)
   int Sp_kc, Hp_kc, rows;
   unsigned int* counter;       // [batch][n_blocks * (2 + 2 n_wn)], zeroed before the launch
+  unsigned long long* trace;   // debug: %globaltimer stamps [layer][6 CTA rows][8 events] of the CTAs (0, y, 0); or nullptr
 };
 
 }  // namespace b2

@@ -51,20 +51,23 @@ int launch_conv1d(const ConvParams& p, int batch, int Lmax, cudaStream_t stream)
 // ------------------------------------------------------------------------------------------------
 __global__ void embed_kernel(const long long* __restrict__ ids, const int* __restrict__ lens, int max_tx,
                              const float* __restrict__ emb, int n_vocab, int H, float scale, float* __restrict__ x,
-                             long long x_bs, int x_ld) {
+                             long long x_bs, int x_ld, int* __restrict__ bad_id) {
   const int b = blockIdx.z;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int c = blockIdx.y;
   if (t >= lens[b]) return;
   long long id = ids[(size_t)b * max_tx + t];
-  id = id < 0 ? 0 : (id >= n_vocab ? n_vocab - 1 : id);
+  if (id < 0 || id >= n_vocab) {  // nn.Embedding raises IndexError (glow_tts/models.py:119): flag it, the host throws
+    if (c == 0) atomicExch(bad_id, 1);
+    id = 0;
+  }
   x[(size_t)b * x_bs + (size_t)c * x_ld + t] = emb[(size_t)id * H + c] * scale;
 }
 
 void launch_embed(const long long* ids, const int* lens, int batch, int max_tx, const float* emb, int n_vocab, int H,
-                  float* x, long long x_bs, int x_ld, cudaStream_t s) {
+                  float* x, long long x_bs, int x_ld, int* bad_id, cudaStream_t s) {
   dim3 grid((max_tx + 63) / 64, H, batch);
-  embed_kernel<<<grid, 64, 0, s>>>(ids, lens, max_tx, emb, n_vocab, H, sqrtf((float)H), x, x_bs, x_ld);
+  embed_kernel<<<grid, 64, 0, s>>>(ids, lens, max_tx, emb, n_vocab, H, sqrtf((float)H), x, x_bs, x_ld, bad_id);
   B2_CUDA(cudaGetLastError());
 }
 
@@ -495,6 +498,21 @@ void launch_expand_squeeze(const float* x_m, long long xm_bs, int xm_ld, const i
   dim3 grid((Tymax + 127) / 128, mel, batch);
   expand_squeeze_kernel<<<grid, 128, 0, s>>>(x_m, xm_bs, xm_ld, idx, idx_ld, y_len, eps, eps_bs, eps_ld, noise_scale,
                                              seed, mel, n_sqz, zs, zs_bs, zs_ld);
+  B2_CUDA(cudaGetLastError());
+}
+
+// the production noise stream on its own: eps[b][c][f] exactly as expand_squeeze_kernel draws it (moment tests)
+__global__ void noise_fill_kernel(unsigned long long seed, int mel, int n, float* __restrict__ out, long long out_bs, int out_ld) {
+  const int b = blockIdx.z, c = blockIdx.y;
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n) return;
+  out[(size_t)b * out_bs + (size_t)c * out_ld + f] =
+      philox_normal(seed, ((unsigned long long)b << 40) ^ ((unsigned long long)c << 24) ^ (unsigned long long)f);
+}
+void launch_noise_fill(unsigned long long seed, int batch, int mel, int n, float* out, long long out_bs, int out_ld, cudaStream_t s) {
+  if (n <= 0 || batch <= 0) return;
+  dim3 grid((n + 127) / 128, mel, batch);
+  noise_fill_kernel<<<grid, 128, 0, s>>>(seed, mel, n, out, out_bs, out_ld);
   B2_CUDA(cudaGetLastError());
 }
 

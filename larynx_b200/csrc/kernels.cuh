@@ -19,7 +19,8 @@ void launch_attn_umma(const void* qkv_p, long long qkv_bs, int qkv_kc, int qkv_r
                       int out_ld, cudaStream_t s);
 
 void launch_embed(const long long* ids, const int* lens, int batch, int max_tx, const float* emb, int n_vocab, int H,
-                  float* x, long long x_bs, int x_ld, cudaStream_t s);
+                  float* x, long long x_bs, int x_ld, int* bad_id, cudaStream_t s);
+void launch_noise_fill(unsigned long long seed, int batch, int mel, int n, float* out, long long out_bs, int out_ld, cudaStream_t s);
 void launch_layernorm(const float* x, const float* res, const float* gamma, const float* beta, float* y, long long bs,
                       int ld, int C, const int* lens, int batch, int Lmax, int pre_relu, int post_relu, cudaStream_t s,
                       void* planes = nullptr, long long pl_bs = 0, int pl_kc = 0, int pl_rows = 0, int pl_nsplit = 3);

@@ -6,6 +6,7 @@ libb200tts.so (host or device pointers are both accepted by the library).
 from __future__ import annotations
 
 import ctypes as C
+import os
 import threading
 from typing import Dict, Sequence
 
@@ -54,6 +55,12 @@ class Call:
 
     def set_debug(self, on: bool):
         check(_lib.load().b200tts_call_set_debug(self._h, int(on)))
+
+    def debug_noise(self, seed: int, batch: int, mel: int, n: int) -> np.ndarray:
+        """The production Philox/Box-Muller stream on its own (what decode adds when no eps is injected)."""
+        out = np.zeros((batch, mel, max(n, 1)), dtype=np.float32)
+        check(_lib.load().b200tts_debug_noise(self._h, int(seed) & (2**64 - 1), batch, mel, n, ptr(out), out.shape[2]))
+        return out[:, :, :n]
 
     def set_denoiser(self, strength: float):
         """Denoiser strength of the following vocoder calls on this context (0 = off; larynx/hifi_gan.py:152-166)."""
@@ -177,6 +184,18 @@ def tts_finish(glow: GlowModel, voc: HifiGanModel, call: Call, glue: Glue, noise
                mel_out, mel_ld: int, pcm_f32, pcm_i16, pcm_ld: int):
     check(_lib.load().b200tts_tts_finish(glow._h, voc._h, call._h, C.byref(glue), float(noise_scale), ptr(eps), int(eps_ld), int(seed),
                                          ptr(mel_out), int(mel_ld), ptr(pcm_f32), ptr(pcm_i16), int(pcm_ld)))
+
+
+def fresh_seed() -> int:
+    """A 64-bit seed nobody else has: the reference draws fresh torch.randn_like noise per call (glow_tts/models.py:348)."""
+    return int.from_bytes(os.urandom(8), "little")
+
+
+def check_ids(ids: np.ndarray, num_symbols: int):
+    """nn.Embedding raises IndexError for ids outside the table (glow_tts/models.py:119); so do we, before any launch."""
+    if ids.size and (int(ids.min()) < 0 or int(ids.max()) >= num_symbols):
+        raise IndexError(f"phoneme id out of range for this voice: ids must be in [0, {num_symbols}), got "
+                         f"[{int(ids.min())}, {int(ids.max())}]")
 
 
 def pad_ids(id_rows: Sequence[np.ndarray]):

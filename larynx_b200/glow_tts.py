@@ -8,10 +8,10 @@ Extra, optional settings: `eps` (injected N(0,1) noise [80, >=T_y], for parity t
 """
 from __future__ import annotations
 
-import itertools
 import json
 import logging
 import os
+import threading
 import typing
 from pathlib import Path
 
@@ -19,7 +19,7 @@ import numpy as np
 
 from . import pack
 from .constants import ARRAY_OR_TENSOR, SettingsType, TextToSpeechModel, TextToSpeechModelConfig
-from .engine import CALLS, GlowModel
+from .engine import CALLS, GlowModel, check_ids, fresh_seed
 
 _LOGGER = logging.getLogger("larynx_b200.glow_tts")
 
@@ -50,7 +50,9 @@ class GlowTextToSpeech(TextToSpeechModel):
         self.model = GlowModel(blob, self.device)
         self.noise_scale = 0.667
         self.length_scale = 1.0
-        self._seed = itertools.count(1)
+        self._seed_base = fresh_seed()  # per instance (process, rank, model): default noise never repeats across them
+        self._seed_lock = threading.Lock()
+        self._seed_next = 0
 
     # ---------------------------------------------------------------------------------------
     def phonemes_to_mels(self, phoneme_ids: np.ndarray, settings: typing.Optional[SettingsType] = None) -> ARRAY_OR_TENSOR:
@@ -68,6 +70,7 @@ class GlowTextToSpeech(TextToSpeechModel):
         ids = np.ascontiguousarray(np.asarray(phoneme_ids, dtype=np.int64).reshape(1, -1))
         if ids.shape[1] == 0:
             return np.zeros((1, self.model.mel_channels, 0), dtype=np.float32)
+        check_ids(ids, self.model.num_symbols)
         x_len = np.array([ids.shape[1]], dtype=np.int32)
         call = CALLS.get(self.device)
         y_len = self.model.encode(call, ids, x_len, 1, ids.shape[1], length_scale)
@@ -80,5 +83,11 @@ class GlowTextToSpeech(TextToSpeechModel):
             eps = np.ascontiguousarray(np.asarray(eps, dtype=np.float32)[:, :t_y])
             assert eps.shape == (self.model.mel_channels, t_y), "eps must be [mel, >= T_y]"
             eps_ld = t_y
-        self.model.decode(call, mel, t_y, noise_scale, eps, eps_ld, int(seed) if seed is not None else next(self._seed))
+        self.model.decode(call, mel, t_y, noise_scale, eps, eps_ld, int(seed) if seed is not None else self.next_seed())
         return mel
+
+    def next_seed(self) -> int:
+        """Seed of the next default-noise call: instance base + call counter (explicit `seed` settings bypass it)."""
+        with self._seed_lock:
+            self._seed_next += 1
+            return (self._seed_base + self._seed_next) & (2**64 - 1)

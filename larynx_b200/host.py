@@ -81,15 +81,20 @@ def sentence_task(phoneme_ids, glue: MelGlue, tts_model, tts_settings, vocoder_m
 
 
 def synthesize_batch(tts_model, vocoder_model, glue: MelGlue, id_rows: Sequence[np.ndarray], noise_scale: float = 0.667,
-                     length_scale: float = 1.0, eps: Optional[np.ndarray] = None, seed: int = 0, want_mel: bool = False,
-                     want_float: bool = False, denoiser_strength: float = 0.0):
+                     length_scale: float = 1.0, eps: Optional[np.ndarray] = None, seed: Optional[int] = None, want_mel: bool = False,
+                     want_float: bool = False, denoiser_strength: float = 0.0, call=None):
     """Fused path: ids -> PCM for a ragged batch without leaving the device between the passes
     (b200tts_glow_encode + b200tts_tts_finish).  Returns a list of int16 arrays (+ mels / float pcm).
     `denoiser_strength` > 0 runs the spectral-subtraction denoiser (larynx/hifi_gan.py:158-179) on the device
-    after the vocoder, per item."""
+    after the vocoder, per item.  `seed` None draws a fresh noise stream (like the reference's torch.randn_like per call);
+    `call` overrides the calling thread's own call context (the scheduler's workers pass theirs)."""
     g, v = tts_model.model, vocoder_model.model
-    call = engine.CALLS.get(g.device)
+    if call is None:
+        call = engine.CALLS.get(g.device)
+    if seed is None:
+        seed = tts_model.next_seed() if hasattr(tts_model, "next_seed") else engine.fresh_seed()
     ids, x_len = engine.pad_ids(id_rows)
+    engine.check_ids(ids, g.num_symbols)
     b = len(id_rows)
     y_len = g.encode(call, ids, x_len, b, ids.shape[1], length_scale)
     ty = int(y_len.max()) if b else 0
@@ -104,7 +109,7 @@ def synthesize_batch(tts_model, vocoder_model, glue: MelGlue, id_rows: Sequence[
         eps_ld = eps.shape[2]
     call.set_denoiser(denoiser_strength)
     try:
-        engine.tts_finish(g, v, call, glue.c_struct(), noise_scale, eps, eps_ld, seed, mel, mel.shape[2] if want_mel else 0,
+        engine.tts_finish(g, v, call, glue.c_struct(), noise_scale, eps, eps_ld, int(seed) & (2**64 - 1), mel, mel.shape[2] if want_mel else 0,
                           pcm_f32, pcm_i16, pcm_i16.shape[1])
     finally:
         call.set_denoiser(0.0)

@@ -51,6 +51,19 @@ def fold_weight_norm(sd: SD, prefix: str) -> Tensor:
     return v * (g / norm)
 
 
+def prefold(sd: SD, keep_runtime=(".start",)) -> SD:
+    """Fold weight-norm ONCE, as the reference does at load (WN.remove_weight_norm glow_tts/layers.py:164-170 via
+    store_inverse, Generator.remove_weight_norm hifi_gan/models.py:204-211).  CouplingBlock.start keeps its weight-norm
+    at run time in the reference (glow_tts/attentions.py:100-102), so it stays unfolded here too.  Timing runs use this."""
+    out = dict(sd)
+    for k in sd:
+        if k.endswith(".weight_v"):
+            prefix = k[: -len(".weight_v")]
+            if not any(prefix.endswith(sfx) for sfx in keep_runtime):
+                out[prefix + ".weight"] = fold_weight_norm(sd, prefix)
+    return out
+
+
 def channel_layer_norm(x: Tensor, gamma: Tensor, beta: Tensor, eps: float = 1e-4) -> Tensor:
     """glow_tts/layers.py:19-28 — LN over dim 1 (channels), biased variance, eps 1e-4."""
     mean = x.mean(1, keepdim=True)

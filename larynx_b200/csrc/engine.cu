@@ -15,6 +15,7 @@
 #include <string>
 #include <vector>
 
+#include "enc_chain_params.cuh"
 #include "flow_chain_params.cuh"
 #include "kernels.cuh"
 
@@ -179,7 +180,8 @@ static ConvW conv_w(const Weights& W, const std::string& name, int cin, int cout
   c.cin = cin;
   c.cout = cout;
   c.k = k;
-  c.w = W.get(name + ".w", (size_t)cin * cout * k * mult);
+  // fp32 [Cin][K][Cout] copy for the SIMT cross-check path: only in blobs packed for it (pack.want_simt_weights)
+  c.w = W.has(name + ".w") ? W.get(name + ".w", (size_t)cin * cout * k * mult) : nullptr;
   c.b = W.get(name + ".b", cout);
   if (mult == 1) bind_umma(W, name, c);
   return c;
@@ -230,6 +232,8 @@ struct b200tts_call {
   std::vector<int> y_len_h;
   int *xlen_d = nullptr, *ylen_d = nullptr, *sqlen_d = nullptr, *wceil_d = nullptr, *cum_d = nullptr;
   float *logw_d = nullptr, *xm_d = nullptr;
+  // step table of the chained encoder (enc_chain.cuh): pinned host staging + device copy, allocated on first use
+  EncStep *enc_steps_h = nullptr, *enc_steps_d = nullptr;
   // decode state
   int *idx_d = nullptr, idx_ld = 0;
   float* taps_d = nullptr;
@@ -299,6 +303,8 @@ static void set_out(ConvParams& p, const Planes& pl, float slope, const Planes* 
 //   simt          fp32 SIMT convs + SIMT attention everywhere (the in-library cross-check of the tensor-core path)
 //   attn_simt     SIMT attention only
 //   no_flow_chain flow decoder as one launch per conv instead of the persistent kernel (flow_chain.cuh)
+//   no_enc_chain  text encoder as one launch per layer instead of the persistent kernel (enc_chain.cuh)
+//   chain_trace   per-layer phase stamps of the persistent kernels on stderr
 //   trace         per-conv %globaltimer phase trace on stderr (single-threaded use; implies no_flow_chain)
 static bool dbg_flag(const char* name) {
   static const std::string flags = [] {
@@ -317,6 +323,10 @@ static bool conv_trace() {
 }
 static bool flow_chain_enabled() {
   static const bool on = !dbg_flag("no_flow_chain") && !dbg_flag("trace") && !dbg_flag("simt");
+  return on;
+}
+static bool enc_chain_enabled() {
+  static const bool on = !dbg_flag("no_enc_chain") && !dbg_flag("trace") && !dbg_flag("simt") && !dbg_flag("attn_simt");
   return on;
 }
 
@@ -481,7 +491,22 @@ static void glow_encode_impl(const b200tts_glow* m, b200tts_call* c, const int64
   if (um) need += 4 * Arena::pad(B * plane_item_bytes(H, prow, 3), 1) + Arena::pad(B * plane_item_bytes(F, prow, 3), 1) +
                   Arena::pad(B * plane_item_bytes(Fd, prow, 3), 1) + Arena::pad(B * plane_item_bytes(3 * H, prow, 3), 1);
   // tcgen05 attention needs the q/k/v image and handles up to 128 phonemes per item; longer batches use the SIMT kernel
+  bool chain = false;
   const bool um_att = um && attn_umma_supported(H, m->n_heads, m->window, max_tx) && !dbg_flag("attn_simt");
+  // the persistent encoder kernel (enc_chain.cuh): every conv on 3-way split images, <= 128 phonemes per item
+  const int n_enc_steps = 8 + 7 * m->n_layers + 4;
+  {
+    bool ok = um_att && enc_chain_enabled() && enc_chain_fits(max_tx) && n_enc_steps <= EC_MAX_STEPS && m->K <= 5;
+    auto good = [&](const ConvW& w) { return w.wu != nullptr && w.nsplit == 3 && w.nt <= 64; };
+    for (int i = 0; i < 3; ++i) ok = ok && good(m->pre_conv[i]);
+    ok = ok && good(m->pre_proj) && good(m->proj_m) && good(m->dp1) && good(m->dp2);
+    ok = ok && (H / 32) % 3 == 0 && (F / 32) % 4 == 0 && (Fd / 32) % 2 == 0 && H <= 256 && Fd <= 256;
+    ok = ok && (m->dp1.cout + m->dp1.nt - 1) / m->dp1.nt * 2 + (m->proj_m.cout + m->proj_m.nt - 1) / m->proj_m.nt <= EC_YT;
+    for (const GlowEnc& e : m->enc) ok = ok && good(e.qkv) && good(e.o) && good(e.ffn1) && good(e.ffn2) && e.relk_img && e.relv_img;
+    chain = ok;
+  }
+  const int part_c = std::max(std::max(H, Fd), 8);
+  if (chain) need += Arena::pad((size_t)4 * B * part_c * ld, 4) + Arena::pad((size_t)B * n_enc_steps, 4);
   c->enc.reserve(need + 4096);
   long long* ids_d = c->enc.take<long long>(B * max_tx);
   c->xlen_d = c->enc.take<int>(B);
@@ -529,8 +554,151 @@ static void glow_encode_impl(const b200tts_glow* m, b200tts_call* c, const int64
     p.lens = lens; p.len_mul = 1; p.Lin = max_tx;
     return p;
   };
-  // embedding * sqrt(H)                                         models.py:119-121
   B2_CUDA(cudaMemsetAsync(bad_id_d, 0, sizeof(int), s));
+  if (chain) {
+    // ---- the whole encoder as one persistent launch: embedding image -> step table -> enc_chain_kernel -> duration head
+    float* PART = c->enc.take<float>((size_t)4 * B * part_c * ld);
+    unsigned int* counters = c->enc.take<unsigned int>((size_t)B * n_enc_steps);
+    launch_embed_image(ids_d, lens, batch, max_tx, m->emb, m->V, H, X, (long long)H * ld, ld, X_p.ptr, X_p.bs, X_p.kc, X_p.rows,
+                       bad_id_d, s);
+    c->launches++;
+    if (!c->enc_steps_h) {
+      B2_CUDA(cudaMallocHost((void**)&c->enc_steps_h, sizeof(EncStep) * EC_MAX_STEPS));
+      B2_CUDA(cudaMalloc((void**)&c->enc_steps_d, sizeof(EncStep) * EC_MAX_STEPS));
+    }
+    EncStep* st = c->enc_steps_h;
+    memset(st, 0, sizeof(EncStep) * EC_MAX_STEPS);
+    int ns = 0;
+    const long long part_stride = (long long)B * part_c * ld;  // floats between K-split partial buffers
+    auto img = [](const Planes& pl) { return (unsigned char*)pl.ptr; };
+    // conv -> raw fp32 partials (K-split `ksplit`) at CTA rows y0..
+    auto conv_partial = [&](EncConvOp& o, const ConvW& w, const Planes& in, int pad, int ksplit, int y0) {
+      o.w = w.wu; o.bias = nullptr; o.Cin = w.cin; o.Cout = w.cout; o.K = w.k; o.pad = pad; o.NT = w.nt;
+      o.ntiles = (w.cout + w.nt - 1) / w.nt; o.ksplit = ksplit; o.y0 = y0; o.act = ACT_NONE;
+      o.xp = img(in); o.xp_bs = in.bs; o.xp_kc = in.kc;
+      o.y = PART; o.y_bs = (long long)part_c * ld; o.part_stride = part_stride; o.y_ld = ld;
+    };
+    // conv -> operand image (+ bias, activation)
+    auto conv_image = [&](EncConvOp& o, const ConvW& w, const Planes& in, int pad, int act, const Planes& out, int y0) {
+      o.w = w.wu; o.bias = w.b; o.Cin = w.cin; o.Cout = w.cout; o.K = w.k; o.pad = pad; o.NT = w.nt;
+      o.ntiles = (w.cout + w.nt - 1) / w.nt; o.ksplit = 1; o.y0 = y0; o.act = act;
+      o.xp = img(in); o.xp_bs = in.bs; o.xp_kc = in.kc;
+      o.yp = img(out); o.yp_bs = out.bs; o.yp_kc = out.kc;
+    };
+    auto reduce = [&](int parts, int C, const float* bias, const float* res, const float* g, const float* bta, int pre_relu,
+                      int post_relu, float* y, const Planes* out) {  // res / y: [batch][C][ld]
+      EncStep& e = st[ns++];
+      e.type = ES_REDUCE;
+      EncReduceOp& r = e.red;
+      r.x = PART; r.x_bs = (long long)part_c * ld; r.part_stride = part_stride; r.ld = ld; r.parts = parts; r.C = C;
+      r.pre_relu = pre_relu; r.post_relu = post_relu; r.bias = bias; r.res = res; r.res_bs = (long long)C * ld;
+      r.gamma = g; r.beta = bta; r.y = y; r.y_bs = (long long)C * ld;
+      if (out) { r.yp = img(*out); r.yp_bs = out->bs; r.yp_kc = out->kc; }
+    };
+    // prenet: 3 x (conv k5 -> LN -> ReLU), 1x1 proj + residual              layers.py:73-80
+    for (int i = 0; i < 3; ++i) {
+      EncStep& e = st[ns++];
+      e.type = ES_CONV; e.n_conv = 1;
+      conv_partial(e.conv[0], m->pre_conv[i], i == 0 ? X_p : P_p[(i - 1) & 1], 2, 3, 0);
+      reduce(3, H, m->pre_conv[i].b, nullptr, m->pre_lng[i], m->pre_lnb[i], 0, 1, nullptr, &P_p[i & 1]);
+    }
+    {
+      EncStep& e = st[ns++];
+      e.type = ES_CONV; e.n_conv = 1;
+      conv_partial(e.conv[0], m->pre_proj, P_p[0], 0, 3, 0);
+      reduce(3, H, m->pre_proj.b, X, nullptr, nullptr, 0, 0, X, &X_p);
+    }
+    // encoder layers                                                          attentions.py:62-74
+    for (int i = 0; i < m->n_layers; ++i) {
+      const GlowEnc& L = m->enc[i];
+      {
+        EncStep& e = st[ns++];
+        e.type = ES_CONV; e.n_conv = 1;
+        conv_image(e.conv[0], L.qkv, X_p, 0, ACT_NONE, QKV_p, 0);
+      }
+      {
+        EncStep& e = st[ns++];
+        e.type = ES_ATTN;
+        EncAttnOp& a = e.att;
+        a.qkv_p = img(QKV_p); a.qkv_bs = QKV_p.bs; a.qkv_kc = QKV_p.kc;
+        a.relk_img = (const unsigned char*)L.relk_img; a.relv_img = (const unsigned char*)L.relv_img;
+        a.window = m->window; a.H = H; a.n_heads = m->n_heads; a.y0 = 0;
+        a.out_p = img(ATT_p); a.out_bs = ATT_p.bs; a.out_kc = ATT_p.kc;
+      }
+      {
+        EncStep& e = st[ns++];
+        e.type = ES_CONV; e.n_conv = 1;
+        conv_partial(e.conv[0], L.o, ATT_p, 0, 3, m->n_heads);  // not on the attention CTAs: their weight ring was on hold
+        reduce(3, H, L.o.b, X, L.ln1g, L.ln1b, 0, 0, X, &X_p);
+      }
+      {
+        EncStep& e = st[ns++];
+        e.type = ES_CONV; e.n_conv = 1;
+        conv_image(e.conv[0], L.ffn1, X_p, m->K / 2, ACT_RELU, FF_p, 0);
+      }
+      {
+        EncStep& e = st[ns++];
+        e.type = ES_CONV; e.n_conv = 1;
+        conv_partial(e.conv[0], L.ffn2, FF_p, m->K / 2, 4, 0);
+        reduce(4, H, L.ffn2.b, X, L.ln2g, L.ln2b, 0, 0, X, &X_p);
+      }
+    }
+    // proj_m and the duration predictor                                        models.py:133, 39-49
+    {
+      EncStep& e = st[ns++];
+      e.type = ES_CONV; e.n_conv = 2;
+      conv_partial(e.conv[0], m->dp1, X_p, m->K / 2, 2, 0);
+      EncConvOp& pm = e.conv[1];
+      pm.w = m->proj_m.wu; pm.bias = m->proj_m.b; pm.Cin = H; pm.Cout = mel; pm.K = 1; pm.pad = 0; pm.NT = m->proj_m.nt;
+      pm.ntiles = (mel + pm.NT - 1) / pm.NT; pm.ksplit = 1; pm.y0 = e.conv[0].ntiles * 2; pm.act = ACT_NONE;
+      pm.xp = img(X_p); pm.xp_bs = X_p.bs; pm.xp_kc = X_p.kc;
+      pm.y = c->xm_d; pm.y_bs = (long long)mel * ld; pm.y_ld = ld;
+      reduce(2, Fd, m->dp1.b, nullptr, m->dp_ln1g, m->dp_ln1b, 1, 0, nullptr, &D1_p);
+    }
+    {
+      EncStep& e = st[ns++];
+      e.type = ES_CONV; e.n_conv = 1;
+      conv_partial(e.conv[0], m->dp2, D1_p, m->K / 2, 2, 0);
+      reduce(2, Fd, m->dp2.b, nullptr, m->dp_ln2g, m->dp_ln2b, 1, 0, D2, nullptr);
+    }
+    B2_CHECK(ns == n_enc_steps, "encoder step table has an unexpected length");
+    B2_CUDA(cudaMemcpyAsync(c->enc_steps_d, st, sizeof(EncStep) * ns, cudaMemcpyHostToDevice, s));
+    EncChainParams fp;
+    memset(&fp, 0, sizeof(fp));
+    fp.steps = c->enc_steps_d; fp.n_steps = ns; fp.batch = batch; fp.rows = prow; fp.lens = lens; fp.counter = counters;
+    static const bool trace = dbg_flag("chain_trace");
+    if (trace) {
+      static unsigned long long* tr = nullptr;
+      if (!tr) B2_CUDA(cudaMallocManaged(&tr, sizeof(unsigned long long) * 8 * EC_YT * EC_MAX_STEPS));
+      B2_CUDA(cudaDeviceSynchronize());
+      memset(tr, 0, sizeof(unsigned long long) * 8 * EC_YT * EC_MAX_STEPS);
+      fp.trace = tr;
+      c->launches += launch_enc_chain(st, fp, max_tx, s);
+      B2_CUDA(cudaDeviceSynchronize());
+      unsigned long long t_start = ~0ull, t_end = 0;
+      for (int i = 0; i < 8 * EC_YT * ns; ++i)
+        if (tr[i]) { t_start = std::min(t_start, tr[i]); t_end = std::max(t_end, tr[i]); }
+      for (int L = 0; L < ns && L < 16; ++L) {  // prenet + first layer
+        fprintf(stderr, "[enc] S%2d type %d:", L, st[L].type);
+        for (int y = 0; y < EC_YT; ++y) {
+          const unsigned long long* e = tr + ((size_t)L * EC_YT + y) * 8;
+          if (!e[5]) continue;
+          fprintf(stderr, " | y%d start %6.2f A %5.2f mma %5.2f acc %5.2f epi %5.2f pub %5.2f", y, ((e[0] ? e[0] : e[4]) - t_start) * 1e-3,
+                  e[0] && e[1] ? (e[1] - e[0]) * 1e-3 : 0.0, e[3] && e[1] ? (e[3] - e[1]) * 1e-3 : 0.0, e[3] ? (e[4] - e[3]) * 1e-3 : 0.0,
+                  (e[5] - e[4]) * 1e-3, (e[6] - e[5]) * 1e-3);
+        }
+        fprintf(stderr, "\n");
+      }
+      fprintf(stderr, "[enc] %d steps, %.1f us from first stamp to last publish (%.2f us per step)\n", ns, (t_end - t_start) * 1e-3,
+              (t_end - t_start) * 1e-3 / ns);
+    } else {
+      c->launches += launch_enc_chain(st, fp, max_tx, s);
+    }
+    launch_duration(D2, (long long)Fd * ld, ld, Fd, m->dp_pw, m->dp_pb, lens, batch, max_tx, length_scale, m->n_sqz,
+                    c->logw_d, c->wceil_d, c->cum_d, c->ylen_d, s);
+    c->launches += 1;
+  } else {
+  // embedding * sqrt(H)                                         models.py:119-121
   launch_embed(ids_d, lens, batch, max_tx, m->emb, m->V, H, X, (long long)H * ld, ld, bad_id_d, s);
   c->launches++;
   // prenet: 3 x (conv k5 -> LN -> ReLU), 1x1 proj + residual   layers.py:73-80
@@ -612,6 +780,7 @@ static void glow_encode_impl(const b200tts_glow* m, b200tts_call* c, const int64
                     c->logw_d, c->wceil_d, c->cum_d, c->ylen_d, s);
     c->launches += 1;
   }
+  }  // classic (one launch per layer) path
   c->y_len_h.resize(batch);
   B2_CUDA(cudaMemcpyAsync(c->y_len_h.data(), c->ylen_d, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
   int bad_id = 0;
@@ -1328,6 +1497,7 @@ int b200tts_call_create(int device, b200tts_call** out) {
   attention_init_attributes();
   attn_umma_init_attributes();
   flow_chain_init_attributes();
+  enc_chain_init_attributes();
   b200tts_call* c = new b200tts_call();
   c->device = device;
   B2_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -1352,6 +1522,8 @@ int b200tts_call_destroy(b200tts_call* c) {
     cudaStreamDestroy(c->aux[i]);
     cudaEventDestroy(c->join[i]);
   }
+  cudaFreeHost(c->enc_steps_h);
+  cudaFree(c->enc_steps_d);
   cudaStreamDestroy(c->stream);
   cudaEventDestroy(c->fork);
   cudaEventDestroy(c->ev0);

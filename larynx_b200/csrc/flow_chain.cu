@@ -13,7 +13,7 @@ void flow_chain_init_attributes() {
 // geometry the kernel is built for (every released voice: SURVEY.md §2.2); anything else takes the per-layer launches
 bool flow_chain_geometry_ok(int half, int Hd, int K, int dil_rate, int n_wn, int nt_hidden, int nt_end) {
   if (Hd != FC_NT * FC_YT / 2 || nt_hidden != FC_NT) return false;
-  if (n_wn < 1 || n_wn > FC_MAX_WN || K < 1 || K > FC_G) return false;
+  if (n_wn < 1 || n_wn > FC_MAX_WN || K < 1 || K > FC_KMAX) return false;
   int dil = 1;
   for (int l = 1; l < n_wn; ++l) dil *= dil_rate;
   if ((K - 1) * dil > FC_HALO || (K * dil - dil) / 2 > UM_PADL) return false;

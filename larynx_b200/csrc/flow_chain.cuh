@@ -28,16 +28,46 @@ namespace b2 {
 constexpr int FC_NT = 64;      // N tile of start / in / res_skip (pack.py: B200TTS_GLOW_NT)
 constexpr int FC_YT = 6;       // channel-tile CTAs per time tile = 2 * Hd / FC_NT
 constexpr int FC_EW = 8;       // epilogue warps
-constexpr int FC_G = 5;        // taps per weight slot (one bulk copy per 32-channel chunk of an in_layer)
-constexpr int FC_WST = 3, FC_AST = 4;
+constexpr int FC_KMAX = 5;     // taps of an in_layer (bounded so that the geometry check is explicit)
+constexpr int FC_G1 = 3;       // 1x1 convs: 32-channel chunks per weight slot
+constexpr int FC_WST = 3;      // weight ring slots of FC_KMAX blocks (40 KB): one chunk with all its taps (in_layer) or FC_G1
+                               // chunks of a 1x1 conv.  Per slot the MMA warp pays one wait and one commit; with one block
+                               // per slot that fixed cost (~150 clk) exceeded the 4 MMAs it paid for (measured: 6.9 vs 4.8 us)
+constexpr int FC_AST = 4;
 constexpr int FC_HALO = 16;    // max (K-1)*dil
 constexpr int FC_RA = 128 + FC_HALO;
 constexpr int FC_THREADS = FC_EW * 32 + 96;
 constexpr uint32_t FC_A_SPLIT = UM_KCH * FC_RA * 16;
 constexpr uint32_t FC_A_STAGE = 2 * FC_A_SPLIT;
-constexpr uint32_t FC_W_SLOT = (uint32_t)FC_G * 2 * UM_KCH * FC_NT * 16;
-constexpr size_t FC_SMEM = (size_t)FC_AST * FC_A_STAGE + (size_t)FC_WST * FC_W_SLOT + 512 + sizeof(ConvParams) + 16 +
-                           4 * (64 + 64 + 16 + 2 * 256);
+constexpr uint32_t FC_W_SLOT = (uint32_t)FC_KMAX * 2 * UM_KCH * FC_NT * 16;
+constexpr size_t FC_SMEM = (size_t)FC_AST * FC_A_STAGE + (size_t)FC_WST * FC_W_SLOT + 512 + 4 * (64 + 64 + 16 + 2 * 256);
+
+// The fields conv_umma_epilogue.inc reads from `p`, for this kernel: register-resident, and everything the flow never uses
+// is a compile-time constant so that the shared epilogue text collapses to the one mode it is instantiated for.
+template <int EPI>
+struct FlowEpiP {
+  static constexpr int epi = EPI, pix = 1, act = ACT_NONE, yp_nsplit = 2, split = 0, first = 0;
+  static constexpr float yp_slope = 1.f, rp_inv_slope = 1.f;
+  static constexpr const void* rp = nullptr;
+  static constexpr long long rp_bs = 0;
+  static constexpr int rp_kc = 0, rp_rows = 0;
+  static constexpr const float* res = nullptr;
+  static constexpr long long res_bs = 0;
+  static constexpr int res_ld = 0;
+  static constexpr float* aux = nullptr;
+  static constexpr long long aux_bs = 0;
+  static constexpr int aux_ld = 0;
+  static constexpr void* yp2 = nullptr;
+  static constexpr unsigned long long* dbg = nullptr;
+  void* yp;
+  long long yp_bs;
+  int yp_kc, yp_rows;
+  float* y;
+  long long y_bs;
+  int y_ld;
+  float* tap;
+  int half, Cout;
+};
 
 enum FlowStepKind { FS_START = 0, FS_IN = 1, FS_RS = 2, FS_RS_LAST = 3, FS_END = 4 };
 
@@ -130,12 +160,12 @@ __global__ void __launch_bounds__(FC_THREADS, 1) flow_chain_kernel(const __grid_
   uint64_t* a_full = bars;          // [AST]
   uint64_t* a_empty = bars + 4;     // [AST]
   uint64_t* w_full = bars + 8;      // [WST]
-  uint64_t* w_empty = bars + 12;    // [WST]
-  uint64_t* acc_full = bars + 16;   // MMA -> epilogue
-  uint64_t* acc_empty = bars + 17;  // epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
-  ConvParams* s_p = reinterpret_cast<ConvParams*>(bars + 64);  // epilogue parameters of the current step (conv_umma_epilogue.inc)
-  float* s_wbias = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(s_p) + ((sizeof(ConvParams) + 15) & ~(size_t)15));
+  uint64_t* w_empty = bars + 24;    // [WST]
+  uint64_t* acc_full = bars + 40;   // MMA -> epilogue
+  uint64_t* acc_empty = bars + 41;  // epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 42);
+  static_assert(FC_WST <= 16 && FC_AST <= 4, "barrier slots");
+  float* s_wbias = reinterpret_cast<float*>(bars + 64);
   float* s_pbias = s_wbias + 64;    // running bias of the persistent accumulator (sum of the biases accumulated so far)
   float* s_inv = s_pbias + 64;
   float* s_anb = s_inv + 16;
@@ -180,14 +210,15 @@ __global__ void __launch_bounds__(FC_THREADS, 1) flow_chain_kernel(const __grid_
             if (!st.active) continue;
             const uint32_t w_stage = (uint32_t)NSPLIT * UM_KCH * st.NT * 16;
             const unsigned char* gw = reinterpret_cast<const unsigned char*>(fb.w[step]) + (size_t)st.wt * st.nch * st.K * w_stage;
-            for (int c = 0; c < st.nch; ++c)
-              for (int k0 = 0; k0 < st.K; k0 += FC_G) {
-                const uint32_t bytes = (uint32_t)min(FC_G, st.K - k0) * w_stage;
-                mbar_wait(&w_empty[s], ph);
-                mbar_arrive_expect_tx(&w_full[s], bytes);
-                bulk_g2s(sW + (size_t)s * w_slot, gw + ((size_t)c * st.K + k0) * w_stage, bytes, &w_full[s]);
-                if (++s == FC_WST) { s = 0; ph ^= 1; }
-              }
+            const int n_blocks = st.nch * st.K;  // (chunk, tap) blocks are consecutive in the image
+            const int G = st.K > 1 ? st.K : FC_G1;
+            for (int i = 0; i < n_blocks; i += G) {
+              const uint32_t bytes = (uint32_t)min(G, n_blocks - i) * w_stage;
+              mbar_wait(&w_empty[s], ph);
+              mbar_arrive_expect_tx(&w_full[s], bytes);
+              bulk_g2s(sW + (size_t)s * w_slot, gw + (size_t)i * w_stage, bytes, &w_full[s]);
+              if (++s == FC_WST) { s = 0; ph ^= 1; }
+            }
           }
         }
       }
@@ -212,8 +243,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) flow_chain_kernel(const __grid_
                 // every CTA of this utterance has finished (and published) layer L-1 — and with it, in order, all earlier ones
                 unsigned int spins = 0;
                 while (fc_ld_acquire(cnt + (L - 1)) < prev_expect) {
-                  __nanosleep(20);
-                  if (++spins > (1u << 24)) {  // seconds: a lost arrival must fail loudly, not hang the device
+                  if (++spins > (1u << 25)) {  // seconds: a lost arrival must fail loudly, not hang the device
                     printf("flow_chain: barrier %d of item %d timed out (CTA %d,%d,%d)\n", L - 1, b, blockIdx.x, blockIdx.y, blockIdx.z);
                     __trap();
                   }
@@ -260,45 +290,61 @@ __global__ void __launch_bounds__(FC_THREADS, 1) flow_chain_kernel(const __grid_
           const FlowStep st = flow_step(fp, step, y);
           if (!st.active) continue;  // uniform across the warp
           const int NT = st.NT, K = st.K, dil = st.dil, nch = st.nch;
-          const uint32_t w_stage = (uint32_t)NSPLIT * UM_KCH * NT * 16;
           const uint32_t idesc1 = make_idesc_bf16_f32(128, NT), idesc2 = make_idesc_bf16_f32(128, 2 * NT);
           const uint64_t b_desc0 = make_smem_desc(smem_u32(sW), NSPLIT * NT * 16, 128);
           const uint32_t b_ks = (2 * NSPLIT * NT * 16) >> 4;
           const uint32_t tm = tmem + (st.acc ? 128u : 0u);
           mbar_wait(acc_empty, (use & 1) ^ 1);  // the epilogue of this CTA's previous step is done with the accumulators
           tc_fence_after();
-          for (int c = 0; c < nch; ++c) {
-            mbar_wait(&a_full[as], aph);
-            tc_fence_after();
-            if (c == 0 && lane == 0) FC_TRACE(blk * n_steps + step, 1);
-            const uint64_t a_c = a_desc0 + ((as * a_stage) >> 4);
-            for (int k0 = 0; k0 < K; k0 += FC_G) {
+          const uint32_t w_stage = (uint32_t)NSPLIT * UM_KCH * NT * 16;
+          auto issue = [&](uint64_t a_k, uint64_t b_k, uint32_t first) {  // both K=16 steps of one (chunk, tap) block
+#pragma unroll
+            for (int ks = 0; ks < UM_BKC / 16; ++ks) {
+              const uint64_t a0 = a_k + ks * a_ks, b0 = b_k + ks * b_ks;
+              const uint32_t acc0 = ks == 0 ? first : 1u;
+              mma_bf16_ss(tm, a0, b0, idesc2, acc0);            // hi x [hi|lo] -> [c0|c1]
+              mma_bf16_ss(tm + NT, a0 + a_sp, b0, idesc1, 1u);  // lo x hi      -> c1
+            }
+          };
+          if (K > 1) {  // in_layer: a weight slot = one chunk with all its taps
+            for (int c = 0; c < nch; ++c) {
+              mbar_wait(&a_full[as], aph);
+              tc_fence_after();
+              if (c == 0 && lane == 0) FC_TRACE(blk * n_steps + step, 1);
               mbar_wait(&w_full[ws], wph);
               tc_fence_after();
-              if (c == 0 && k0 == 0 && lane == 0) FC_TRACE(blk * n_steps + step, 2);
-              const int cnt = min(FC_G, K - k0);
+              if (c == 0 && lane == 0) FC_TRACE(blk * n_steps + step, 2);
               if (elect_one()) {
-                for (int kk = 0; kk < cnt; ++kk) {
-                  const int k = k0 + kk;
-                  const uint64_t a_k = a_c + (uint32_t)(k * dil);
-                  const uint64_t b_k = b_desc0 + ((ws * w_slot + kk * w_stage) >> 4);
-                  const uint32_t first = (c == 0 && k == 0 && st.init) ? 0u : 1u;
-#pragma unroll
-                  for (int ks = 0; ks < UM_BKC / 16; ++ks) {
-                    const uint64_t a0 = a_k + ks * a_ks, b0 = b_k + ks * b_ks;
-                    const uint32_t acc0 = ks == 0 ? first : 1u;
-                    mma_bf16_ss(tm, a0, b0, idesc2, acc0);            // hi x [hi|lo] -> [c0|c1]
-                    mma_bf16_ss(tm + NT, a0 + a_sp, b0, idesc1, 1u);  // lo x hi      -> c1
-                  }
-                }
+                const uint64_t a_c = a_desc0 + ((as * a_stage) >> 4);
+                for (int k = 0; k < K; ++k)
+                  issue(a_c + (uint32_t)(k * dil), b_desc0 + ((ws * w_slot + k * w_stage) >> 4), (c == 0 && k == 0 && st.init) ? 0u : 1u);
                 mma_commit(&w_empty[ws]);
+                mma_commit(&a_empty[as]);
               }
               __syncwarp();
               if (++ws == FC_WST) { ws = 0; wph ^= 1; }
+              if (++as == FC_AST) { as = 0; aph ^= 1; }
             }
-            if (elect_one()) mma_commit(&a_empty[as]);
-            __syncwarp();
-            if (++as == FC_AST) { as = 0; aph ^= 1; }
+          } else {  // 1x1 conv: a weight slot = FC_G1 chunks
+            for (int c0 = 0; c0 < nch; c0 += FC_G1) {
+              mbar_wait(&w_full[ws], wph);
+              tc_fence_after();
+              if (c0 == 0 && lane == 0) FC_TRACE(blk * n_steps + step, 2);
+              const int cnt = min(FC_G1, nch - c0);
+              for (int j = 0; j < cnt; ++j) {
+                mbar_wait(&a_full[as], aph);
+                tc_fence_after();
+                if (c0 + j == 0 && lane == 0) FC_TRACE(blk * n_steps + step, 1);
+                if (elect_one()) {
+                  issue(a_desc0 + ((as * a_stage) >> 4), b_desc0 + ((ws * w_slot + j * w_stage) >> 4), (c0 + j == 0 && st.init) ? 0u : 1u);
+                  mma_commit(&a_empty[as]);
+                  if (j == cnt - 1) mma_commit(&w_empty[ws]);
+                }
+                __syncwarp();
+                if (++as == FC_AST) { as = 0; aph ^= 1; }
+              }
+              if (++ws == FC_WST) { ws = 0; wph ^= 1; }
+            }
           }
           if (elect_one()) mma_commit(acc_full);
           __syncwarp();
@@ -310,7 +356,6 @@ __global__ void __launch_bounds__(FC_THREADS, 1) flow_chain_kernel(const __grid_
     // ===================== epilogue warps =====================
     uint32_t use = 0;
     const int it = 1;  // (tracing in the shared epilogue text is tied to it == 0: off)
-    const ConvParams& p = *s_p;
     for (int b = blockIdx.z; b < fp.batch; b += gridDim.z) {
       const int Lb = fp.lens[b];
       if (t0 >= Lb) continue;
@@ -336,29 +381,28 @@ __global__ void __launch_bounds__(FC_THREADS, 1) flow_chain_kernel(const __grid_
               s_ans[i] = fb.an_scale[i];
             }
           }
-          if (tid == 0 && st.epi >= 0) {
-            ConvParams q;
-            q.epi = st.epi;
-            q.Cout = st.kind == FS_END ? 2 * fp.half : (st.kind == FS_IN ? 2 * fp.Hd : fp.Hd);
-            q.half = fp.half;
-            if (st.kind == FS_END) {
-              q.y = fp.S; q.y_bs = fp.S_bs; q.y_ld = fp.S_ld;
-              q.yp = fp.S_p; q.yp_bs = fp.Sp_bs; q.yp_kc = fp.Sp_kc;
-              if (fp.taps) q.tap = fp.taps + (size_t)fb.tap_index * fp.batch * fp.S_bs;
-            } else {
-              q.yp = st.kind == FS_IN ? fp.A_p : (st.kind == FS_RS_LAST ? fp.K_p : fp.H_p);
-              q.yp_bs = fp.Hp_bs; q.yp_kc = fp.Hp_kc;
-            }
-            q.yp_rows = fp.rows; q.yp_nsplit = 2; q.yp_slope = 1.f;
-            *s_p = q;
-          }
           fc_epi_bar();
           mbar_wait(acc_full, use & 1);
           tc_fence_after();
           if (tid == 0) FC_TRACE(blk * n_steps + step, 4);
-          if (st.epi >= 0) {
-            const uint32_t tm = tmem + (st.acc ? 128u : 0u);
-            const float* s_bias = st.acc ? s_pbias : s_wbias;
+          const uint32_t tm = tmem + (st.acc ? 128u : 0u);
+          const float* s_bias = st.acc ? s_pbias : s_wbias;
+          if (st.epi == EPI_GATE) {  // in_layer: tanh * sigmoid -> operand image of the gate output
+            FlowEpiP<EPI_GATE> p;
+            p.yp = fp.A_p; p.yp_bs = fp.Hp_bs; p.yp_kc = fp.Hp_kc; p.yp_rows = fp.rows;
+            p.y = nullptr; p.y_bs = 0; p.y_ld = 0; p.tap = nullptr; p.half = fp.half; p.Cout = 2 * fp.Hd;
+#include "conv_umma_epilogue.inc"
+          } else if (st.epi == EPI_COUPLING) {  // end: affine coupling + InvConvNear^-1 + ActNorm^-1 on the fp32 state
+            FlowEpiP<EPI_COUPLING> p;
+            p.yp = fp.S_p; p.yp_bs = fp.Sp_bs; p.yp_kc = fp.Sp_kc; p.yp_rows = fp.rows;
+            p.y = fp.S; p.y_bs = fp.S_bs; p.y_ld = fp.S_ld;
+            p.tap = fp.taps ? fp.taps + (size_t)fb.tap_index * fp.batch * fp.S_bs : nullptr;
+            p.half = fp.half; p.Cout = 2 * fp.half;
+#include "conv_umma_epilogue.inc"
+          } else if (st.epi == EPI_PLAIN) {  // persistent accumulator + running bias -> operand image of h / of the skip sum
+            FlowEpiP<EPI_PLAIN> p;
+            p.yp = st.kind == FS_RS_LAST ? fp.K_p : fp.H_p; p.yp_bs = fp.Hp_bs; p.yp_kc = fp.Hp_kc; p.yp_rows = fp.rows;
+            p.y = nullptr; p.y_bs = 0; p.y_ld = 0; p.tap = nullptr; p.half = fp.half; p.Cout = fp.Hd;
 #include "conv_umma_epilogue.inc"
           }
           tc_fence_before();
@@ -366,11 +410,13 @@ __global__ void __launch_bounds__(FC_THREADS, 1) flow_chain_kernel(const __grid_
           if (lane == 0) mbar_arrive(acc_empty);
           ++use;
           if (tid == 0) FC_TRACE(blk * n_steps + step, 5);
-          // publish this CTA's part of the layer: all epilogue warps' global writes, then ONE release increment
-          __threadfence();
-          asm volatile("fence.proxy.async;" ::: "memory");
+          // publish this CTA's part of the layer: the named barrier orders every epilogue thread's global writes before
+          // thread 0, whose gpu-scope release is cumulative over them (the pattern of a cooperative-groups grid barrier)
           fc_epi_bar();
-          if (tid == 0) fc_red_release(cnt + (blk * n_steps + step));
+          if (tid == 0) {
+            asm volatile("fence.proxy.async;" ::: "memory");
+            fc_red_release(cnt + (blk * n_steps + step));
+          }
           if (tid == 0) FC_TRACE(blk * n_steps + step, 6);
         }
       }

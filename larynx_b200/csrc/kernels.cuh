@@ -69,4 +69,13 @@ bool flow_chain_geometry_ok(int half, int Hd, int K, int dil_rate, int n_wn, int
 bool flow_chain_fits(int Lmax);
 int launch_flow_chain(const FlowChainParams& fp, int Lmax, cudaStream_t s);
 
+// the text encoder + duration convs in one persistent cooperative launch (enc_chain.cu)
+struct EncStep;
+struct EncChainParams;
+void enc_chain_init_attributes();
+bool enc_chain_fits(int max_tx);
+int launch_enc_chain(const EncStep* steps, const EncChainParams& fp, int max_tx, cudaStream_t s);
+void launch_embed_image(const long long* ids, const int* lens, int batch, int max_tx, const float* emb, int n_vocab, int H, float* x,
+                        long long x_bs, int x_ld, void* img, long long img_bs, int kc_total, int rows, int* bad_id, cudaStream_t s);
+
 }  // namespace b2

@@ -174,11 +174,12 @@ class BlobWriter:
         self.items.append((name, bits.view(np.float32)))
 
     nt_max = 128
+    simt = False  # also store the fp32 [Cin][K][Cout] copies the SIMT cross-check path reads (B200TTS_DEBUG=simt)
 
-    def add_conv(self, name: str, w: np.ndarray, b: np.ndarray, nsplit: int = 2, simt: bool = True,
+    def add_conv(self, name: str, w: np.ndarray, b: np.ndarray, nsplit: int = 2, simt: Optional[bool] = None,
                  nt_max: Optional[int] = None):
         """w is [Cout][Cin][K] in final (packed) channel order."""
-        if simt:
+        if self.simt if simt is None else simt:
             self.add(name + ".w", conv_layout(w))
         self.add(name + ".b", b)
         img, meta = umma_image(w, nsplit, self.nt_max if nt_max is None else nt_max)
@@ -205,7 +206,15 @@ class BlobWriter:
         return blob
 
 
-def pack_glow(sd: Dict[str, np.ndarray], config: dict) -> np.ndarray:
+def want_simt_weights() -> bool:
+    """The fp32 SIMT conv path is an in-library cross-check (B200TTS_DEBUG=simt); only then do the blobs carry its weights
+    (they double the blob: 243 MB instead of 126 MB per GlowTTS voice)."""
+    import os
+
+    return "simt" in os.environ.get("B200TTS_DEBUG", "").split(",")
+
+
+def pack_glow(sd: Dict[str, np.ndarray], config: dict, simt: Optional[bool] = None) -> np.ndarray:
     """Pack a glow_tts FlowGenerator state-dict (reference key names) for b200tts_glow_create."""
     m = config["model"]
     if m.get("n_speakers", 1) > 1 or m.get("gin_channels", 0) != 0:
@@ -221,6 +230,7 @@ def pack_glow(sd: Dict[str, np.ndarray], config: dict) -> np.ndarray:
            m["n_layers_enc"], m["window_size"], mel, m["n_blocks_dec"], m["kernel_size_dec"], m["dilation_rate"],
            m["n_block_layers"], m["n_sqz"], m["n_split"], Hd]
     bw = BlobWriter(KIND_GLOW, cfg)
+    bw.simt = want_simt_weights() if simt is None else bool(simt)
 
     bw.nt_max = 64  # GlowTTS runs on 1-4 time tiles: favour more N tiles (flow_chain.cuh is built for this tile)
     g = lambda k: _np(sd[k])
@@ -280,7 +290,7 @@ def pack_glow(sd: Dict[str, np.ndarray], config: dict) -> np.ndarray:
     return bw.finish()
 
 
-def pack_hifigan(sd: Dict[str, np.ndarray], config: dict) -> np.ndarray:
+def pack_hifigan(sd: Dict[str, np.ndarray], config: dict, simt: Optional[bool] = None) -> np.ndarray:
     """Pack a hifi_gan Generator state-dict (reference key names) for b200tts_hifigan_create.
     `config` may be nested ({"model": {...}}) or the flat jik876 json (universal_large/config.json)."""
     m = config.get("model", config)
@@ -299,12 +309,14 @@ def pack_hifigan(sd: Dict[str, np.ndarray], config: dict) -> np.ndarray:
         for d, dv in enumerate(rd[j]):
             cfg[28 + j * 3 + d] = dv
     bw = BlobWriter(KIND_HIFIGAN, cfg)
+    bw.simt = want_simt_weights() if simt is None else bool(simt)
     g = lambda k: _np(sd[k])
     rb_nt = 128  # ResBlock output-channel tile (64-wide tiles measured equal within 1 % on B200: fewer CTAs win)
     bw.add_conv("conv_pre", fold_weight_norm(sd, "conv_pre"), g("conv_pre.bias"))
     for i, (u, k) in enumerate(zip(rates, ks)):
         wt = fold_weight_norm(sd, f"ups.{i}")
-        bw.add(f"ups{i}.w", polyphase(wt, u, k))
+        if bw.simt:
+            bw.add(f"ups{i}.w", polyphase(wt, u, k))
         bw.add(f"ups{i}.b", g(f"ups.{i}.bias"))
         # tensor-core form: one 3-tap conv with Cout*u pixel-shuffled output channels
         bw.add_conv(f"ups{i}.ps", pixel_shuffle_conv(wt, u, k), np.repeat(g(f"ups.{i}.bias"), u), simt=False)

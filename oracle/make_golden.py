@@ -113,6 +113,32 @@ def main():
     make_denoiser(gen, a["mel_glued"], outdir)
 
 
+def make_round2(outdir):
+    """Round-2 additions: a voice whose symbol table is not ljspeech's (de-de: num_symbols 54, local/de-de/*-glow_tts/
+    config.json) through the whole reference chain, and the two smaller vocoders on the 128-id benchmark mel."""
+    tmp = Path(tempfile.mkdtemp())
+    meta = dict(hifi_seed=HIFI_SEED, eps_seed=EPS_SEED, noise_scale=NOISE_SCALE, length_scale=LENGTH_SCALE)
+    synth.write_glow_voice(tmp / "glow54", 54, GLOW_SEED + 1)
+    synth.write_hifigan_voice(tmp / "hifi", "universal_large", HIFI_SEED)
+    glow, gen = ref_harness.load_reference_models(tmp / "glow54", tmp / "hifi")
+    ids = synth.bench_ids(47, 54, seed=54)
+    assert ids.max() >= 46, "the vector must use symbols beyond ljspeech's table"
+    c = run_case(glow, gen, ids, synth.glow_config(54)["audio"], taps_at=(0,))
+    c["pcm"] = c["pcm"][::8].copy()
+    np.savez_compressed(outdir / "de54_ids47.npz", **c, glow_seed=np.array(GLOW_SEED + 1), num_symbols=np.array(54),
+                        **{k: np.array(v) for k, v in meta.items()})
+    print("de54_ids47: T_y", c["mel"].shape[1], "ceil margin", float(c["ceil_margin"]), "max id", int(ids.max()))
+    b = np.load(outdir / "bench128.npz")
+    for name in ("vctk_small", "vctk_medium"):
+        synth.write_hifigan_voice(tmp / name, name, HIFI_SEED)
+        _, g2 = ref_harness.load_reference_models(tmp / "glow54", tmp / name)
+        with torch.no_grad():
+            pcm = g2(torch.from_numpy(b["mel_glued"][None])).reshape(-1).numpy()
+        np.savez_compressed(outdir / f"{name}_bench128.npz", pcm=pcm[::16].astype(np.float32).copy(), hifi_seed=np.array(HIFI_SEED),
+                            n_samples=np.array(pcm.shape[0]))
+        print(name, "bench128 pcm std", float(pcm.std()), "absmax", float(np.abs(pcm).max()), "samples", pcm.shape[0])
+
+
 def make_denoiser(gen, mel_glued, outdir):
     """Golden vectors of the spectral-subtraction denoiser made by the reference's own numpy STFT code
     (larynx/audio.py:232-306) in the order larynx/hifi_gan.py:158-203 applies it."""
@@ -143,7 +169,9 @@ def make_denoiser(gen, mel_glued, outdir):
 if __name__ == "__main__":
     import sys
 
-    if "--denoiser-only" in sys.argv:
+    if "--round2" in sys.argv:
+        make_round2(ROOT / "tests" / "golden")
+    elif "--denoiser-only" in sys.argv:
         _tmp = Path(tempfile.mkdtemp())
         synth.write_glow_voice(_tmp / "glow", 46, GLOW_SEED)
         synth.write_hifigan_voice(_tmp / "hifi", "universal_large", HIFI_SEED)

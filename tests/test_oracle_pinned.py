@@ -50,6 +50,34 @@ def test_port_vocoder_variants_match_golden(name):
     assert np.abs(pcm.reshape(-1).numpy() - g["pcm"]).max() <= 2e-5
 
 
+def test_port_matches_golden_other_symbol_table():
+    """A voice that is not ljspeech's shape: num_symbols 54 (de-de), own weights, ids beyond ljspeech's table."""
+    g = _load("de54_ids47.npz")
+    ns = int(g["num_symbols"])
+    assert ns == 54 and g["ids"].max() >= 46
+    eps = synth.seeded_eps(4096, seed=int(g["eps_seed"]))
+    gsd, gcfg = common.oracle_glow_sd(ns, int(g["glow_seed"])), common.glow_cfg(ns)
+    o = port.sentence_task(gsd, gcfg, common.oracle_hifi_sd(), common.hifi_cfg(), g["ids"], float(g["noise_scale"]),
+                           float(g["length_scale"]), eps)
+    assert float(g["ceil_margin"]) > 1e-4
+    assert np.array_equal(o["w_ceil"][0].astype(np.int32), g["w_ceil"])
+    assert np.array_equal(o["idx"][0].astype(np.int32), g["idx"])
+    assert np.abs(o["logw"].reshape(-1) - g["logw"]).max() <= 1e-6
+    assert np.abs(o["mel"][0] - g["mel"]).max() <= 5e-6
+    pcm = port.hifigan_forward(common.oracle_hifi_sd(), common.hifi_cfg(), torch.from_numpy(g["mel_glued"][None])).reshape(-1).numpy()
+    assert np.abs(pcm[::8] - g["pcm"]).max() <= 2e-5
+    assert np.abs(port.float_to_int16(pcm).astype(np.int32) - g["audio"].astype(np.int32)).max() <= 1
+
+
+@pytest.mark.parametrize("name", ["vctk_small", "vctk_medium"])
+def test_port_vocoder_variants_match_golden_at_bench_size(name):
+    g, b = _load(f"{name}_bench128.npz"), _load("bench128.npz")
+    pcm = port.hifigan_forward(common.oracle_hifi_sd(name), common.hifi_cfg(name), torch.from_numpy(b["mel_glued"][None]))
+    pcm = pcm.reshape(-1).numpy()
+    assert pcm.shape[0] == int(g["n_samples"])
+    assert np.abs(pcm[::16] - g["pcm"]).max() <= 2e-5
+
+
 def test_flow_taps_match_golden():
     g = _load("ljspeech_fixture28.npz")
     eps = synth.seeded_eps(4096, seed=int(g["eps_seed"]))

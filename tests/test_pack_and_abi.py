@@ -82,8 +82,12 @@ def test_blob_roundtrip_table():
     off, numel = names["flow0.inv"]
     winv = blob[off : off + 64].view(np.float32).reshape(4, 4)
     assert np.abs(winv @ common.glow_sd_np()["decoder.flows.1.weight"] - np.eye(4)).max() < 1e-5
-    # 28.57 M parameters -> ~114 MB
-    assert 220e6 < blob.nbytes < 320e6  # fp32 SIMT layout + bf16 split images for the tensor-core path
+    # 28.57 M parameters: the default blob holds the bf16 split images of the tensor-core path (2 planes for
+    # the flow decoder, 3 for the text encoder) and no fp32 conv copies; the SIMT cross-check path asks for them explicitly
+    assert not any(k.endswith(".w") and not k.startswith("dp.proj") for k in names), "fp32 conv copies in the default blob"
+    assert 110e6 < blob.nbytes < 160e6, blob.nbytes
+    both = pack.pack_glow(common.glow_sd_np(), cfg, simt=True)
+    assert 220e6 < both.nbytes < 320e6, both.nbytes
 
 
 def test_synth_param_counts():

@@ -138,6 +138,46 @@ def test_vocoder_variants(name):
     assert np.abs(pcm - g["pcm"]).max() <= TOL_PCM
 
 
+def test_other_symbol_table_voice_golden():
+    """BASELINE config 4 serves voices whose `num_symbols` is not ljspeech's 46 (de 54, fr 42, ...): a reference-generated
+    golden for a 54-symbol voice with ids beyond ljspeech's table, through the whole path."""
+    g = np.load(os.path.join(GOLDEN, "de54_ids47.npz"))
+    ns = int(g["num_symbols"])
+    eps = synth.seeded_eps(4096, seed=int(g["eps_seed"]))
+    glow, voc = common.product_glow(ns, int(g["glow_seed"])), common.product_hifi()
+    assert glow.model.num_symbols == 54
+    call = engine.CALLS.get(0)
+    mel = glow.phonemes_to_mels(g["ids"], {"noise_scale": float(g["noise_scale"]), "length_scale": float(g["length_scale"]), "eps": eps})
+    logw, w_ceil, idx = glow.model.alignment(call, 1, len(g["ids"]), mel.shape[2])
+    assert np.array_equal(w_ceil[0], g["w_ceil"]) and np.array_equal(idx[0], g["idx"])
+    assert np.abs(logw[0] - g["logw"]).max() < 5e-5
+    assert np.abs(mel[0] - g["mel"]).max() <= TOL_MEL
+    glue = host.MelGlue.from_config(common.glow_cfg(ns)["audio"])
+    pcm = voc.mels_to_float(glue.apply(mel))
+    assert np.abs(pcm[::8] - g["pcm"]).max() <= TOL_E2E
+    with pytest.raises(IndexError):  # the symbol table is per voice: 54 is out of range here, 53 is not
+        glow.phonemes_to_mels(np.array([1, 54], dtype=np.int64))
+
+
+@pytest.mark.parametrize("name", ["vctk_small", "vctk_medium"])
+def test_vocoder_variants_at_bench_size_and_in_ragged_batches(name):
+    g, b = np.load(os.path.join(GOLDEN, f"{name}_bench128.npz")), np.load(os.path.join(GOLDEN, "bench128.npz"))
+    voc = common.product_hifi(name)
+    pcm = voc.mels_to_float(b["mel_glued"][None])
+    assert pcm.shape[0] == int(g["n_samples"])
+    assert np.abs(pcm[::16] - g["pcm"]).max() <= TOL_PCM
+    # ragged batch (ResBlock2 for vctk_small): every item equals its own per-utterance oracle run, no cross talk
+    rs = np.random.RandomState(7)
+    frames = np.array([33, 12, 50], dtype=np.int32)
+    mel = (rs.randn(3, 80, 50) * 3 - 4).astype(np.float32)
+    out = np.zeros((3, 50 * voc.model.hop), dtype=np.float32)
+    voc.model.infer(engine.CALLS.get(0), mel, frames, 3, 50, out, None, out.shape[1])
+    for i, t in enumerate(frames):
+        ref = port.hifigan_forward(common.oracle_hifi_sd(name), common.hifi_cfg(name), torch.from_numpy(mel[i : i + 1, :, :t])).reshape(-1).numpy()
+        assert np.abs(out[i, : t * voc.model.hop] - ref).max() <= TOL_PCM
+        assert np.all(out[i, t * voc.model.hop :] == 0)
+
+
 def test_ragged_batch_equals_per_utterance():
     glow, voc = common.product_glow(), common.product_hifi()
     rows = [synth.bench_ids(n, seed=s) for n, s in ((33, 1), (64, 2), (5, 3), (47, 4))]
@@ -369,6 +409,36 @@ def test_out_of_range_ids_raise():
     with pytest.raises(Exception):
         glow.model.decode(call, np.zeros((1, 80, 8), np.float32), 8, 0.0, None, 0, 1)
     assert glow.phonemes_to_mels(np.array([3, 4, 45, 5], dtype=np.int64), {"noise_scale": 0.0}).shape[1] == 80
+
+
+def test_voice_directory_constructors_on_pool_threads(tmp_path):
+    """The reference's constructor path (larynx/__init__.py:379-407, 472-508): a config object whose model_path holds
+    config.json + generator.pth, `executor=` for the vocoder, `denoiser_strength` on the config — then `_sentence_task`'s
+    flow from four pool threads.  (tests/test_reference_integration.py drives the same classes through the reference's
+    own factories where the reference exists.)"""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from larynx_b200.constants import TextToSpeechModelConfig, VocoderModelConfig
+    from larynx_b200.glow_tts import GlowTextToSpeech
+    from larynx_b200.hifi_gan import HiFiGanVocoder
+
+    gdir = synth.write_glow_voice(tmp_path / "en-us" / "ljspeech-glow_tts")
+    hdir = synth.write_hifigan_voice(tmp_path / "hifi_gan" / "universal_large")
+    pool = ThreadPoolExecutor(4)
+    tts = GlowTextToSpeech(TextToSpeechModelConfig(model_path=gdir, session_options=None, use_cuda=True, half=False))
+    voc = HiFiGanVocoder(VocoderModelConfig(model_path=hdir, session_options=None, denoiser_strength=0.005), executor=pool)
+    setattr(tts, "phoneme_to_id", {"a": 1})  # larynx/__init__.py:362-363
+    assert voc.denoiser_strength == 0.005
+    glue = host.MelGlue.from_config(common.glow_cfg()["audio"])
+    eps = synth.seeded_eps(512, seed=3)
+    rows = [synth.bench_ids(20 + 5 * i, seed=60 + i) for i in range(8)]
+    # same weights, same seeds as the blob-constructed fixtures: identical results
+    blob_tts, blob_voc = common.product_glow(), common.product_hifi()
+    want = [host.sentence_task(r, glue, blob_tts, {"eps": eps}, blob_voc, {"denoiser_strength": 0.005}).audio for r in rows]
+    got = list(pool.map(lambda r: host.sentence_task(r, glue, tts, {"eps": eps}, voc).audio, rows))
+    for w, g_ in zip(want, got):
+        assert g_.dtype == np.int16 and np.array_equal(w, g_)
+    pool.shutdown()
 
 
 def test_reentrant_from_host_threads():

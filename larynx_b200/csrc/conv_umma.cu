@@ -75,7 +75,8 @@ int launch_conv_umma_batch(const ConvParams* ps, int n, int batch, int Lmax, cud
   for (int i = 0; i < n; ++i) {
     const ConvParams& p = ps[i];
     B2_CHECK(p.wu != nullptr && p.um_nt >= 16 && p.um_nt <= 128 && p.um_nt % 16 == 0, "conv_umma: bad weight image");
-    B2_CHECK((p.K - 1) * p.dil <= UM_HALO, "conv_umma: receptive field too wide");
+    // rows of a tile's bulk copies: from the 8-row boundary below its first row, a whole number of 8-row groups
+    B2_CHECK(((p.K - 1) * p.dil + ((UM_PADL - p.pad_left) & 7) + 7) / 8 * 8 <= UM_HALO, "conv_umma: receptive field too wide");
     B2_CHECK(p.pad_left <= UM_PADL, "conv_umma: left padding too wide");
     B2_CHECK(p.n_phase == 1, "conv_umma: transposed convs are packed as pixel-shuffle convs");
     if (p.xp) B2_CHECK(p.xp_kc >= (p.Cin + 31) / 32 * 4, "conv_umma: input plane image too narrow");

@@ -164,6 +164,43 @@ __device__ __forceinline__ void plane_store4(const PlaneOut& po, int kc, int bof
   }
 }
 
+// Activation tile of one 32-channel chunk = NSPLIT planes x 4 channel groups, each a contiguous run of rows in the producer's
+// plane image: NSPLIT*4 bulk copies of 2-8 KB.  A single lane needs ~100 ns per copy (measured in the persistent GlowTTS
+// kernels, profiles/r2a_chain_trace.log), which exceeds the MMA time of a k = 3 chunk; so a whole warp issues them: lane
+// groups of NSPLIT*4 lanes take consecutive chunks (= consecutive ring stages), one copy per lane.  `as` / `aph` (next
+// stage, parity to wait for on its empty barrier) are warp-uniform ring state and advance by the chunks issued.
+// Bulk copies whose global source is not 128-byte aligned run ~3x slower (measured: 72 copies of 2.3 KB took 7.0 us from
+// row 39 / 38 and 2.5 us from row 40, profiles/r2b_chain_trace.log), so a tile is copied from the 8-row boundary below its
+// first row and the MMA descriptors start `a_row_off(row0)` rows into the stage.
+__device__ __forceinline__ uint32_t a_row_off(long long row0) { return (uint32_t)(row0 & 7); }
+template <int NSPLIT, int AST>
+__device__ __forceinline__ void issue_a_chunks(int lane, int& as, uint32_t& aph, int nch, uint64_t* a_empty, uint64_t* a_full,
+                                               unsigned char* sA, uint32_t a_stage, uint32_t a_split_bytes, int RA,
+                                               const unsigned char* xp, int xp_kc, int xp_rows, long long row0, int rows) {
+  using namespace umma;
+  constexpr int CP = NSPLIT * UM_KCH;                    // copies per chunk
+  constexpr int GR = (32 / CP) < AST ? (32 / CP) : AST;  // chunks per round
+  const int q = lane / CP, j = lane - q * CP;
+  const uint32_t roff = a_row_off(row0);
+  const long long row0a = row0 - roff;
+  const uint32_t kc_bytes = (uint32_t)((rows + (int)roff + 7) & ~7) * 16;
+  for (int c0 = 0; c0 < nch; c0 += GR) {
+    int sq = as + q;
+    uint32_t pq = aph;
+    if (sq >= AST) { sq -= AST; pq ^= 1; }
+    if (q < GR && c0 + q < nch) {
+      mbar_wait(&a_empty[sq], pq);
+      if (j == 0) mbar_arrive_expect_tx(&a_full[sq], CP * kc_bytes);
+      const int sp = j / UM_KCH, kc = j - sp * UM_KCH;
+      bulk_g2s(sA + (size_t)sq * a_stage + sp * a_split_bytes + kc * RA * 16,
+               xp + (((size_t)sp * xp_kc + (c0 + q) * UM_KCH + kc) * xp_rows + row0a) * 16, kc_bytes, &a_full[sq]);
+    }
+    as += min(GR, nch - c0);
+    if (as >= AST) { as -= AST; aph ^= 1; }
+    __syncwarp();
+  }
+}
+
 // MT: 128-row tiles per CTA; NSPLIT: bf16 planes per operand; EW: epilogue/gather warps (8 or 16);
 // WST: weight ring depth.  <1,2,8,3> fits two CTAs per SM (large grids); EW = 16 variants are for small grids
 // where a CTA has the SM to itself and the serial latency of one tile is what matters.
@@ -283,26 +320,17 @@ __global__ void __launch_bounds__(EW * 32 + 64 + (NBUF == 2 ? 32 : 0), EW == 8 ?
     }
   } else if (A_WARP && warp == W_ALOAD) {
     // ===================== A by bulk copy from the producer's plane image (persistent launches) =====================
-    if (lane == 0 && planes_in) {
+    if (planes_in) {
       asm volatile("griddepcontrol.wait;" ::: "memory");  // activations are written by the previous grid
       const unsigned char* xp = reinterpret_cast<const unsigned char*>(p.xp) + (size_t)b * p.xp_bs;
       // only the rows the taps can reach: MT*128 + (K-1)*dil of the RA rows a stage has room for
-      const uint32_t kc_bytes = (uint32_t)(MT * 128 + (K - 1) * dil) * 16;
+      const int rows_used = MT * 128 + (K - 1) * dil;
       int as = 0;
       uint32_t aph = 1;
       for (int mtile = blockIdx.x; mtile < m_tiles; mtile += gstride) {
         const long long row0 = (long long)mtile * (MT * 128) - p.pad_left + UM_PADL;
-        for (int c = 0; c < nch; ++c, as = (as + 1 == AST ? 0 : as + 1), aph ^= (as == 0)) {
-          mbar_wait(&a_empty[as], aph);
-          mbar_arrive_expect_tx(&a_full[as], NSPLIT * UM_KCH * kc_bytes);
-          unsigned char* dst = sA + (size_t)as * a_stage;
-          for (int sp = 0; sp < NSPLIT; ++sp)
-#pragma unroll
-            for (int kc = 0; kc < UM_KCH; ++kc)
-              bulk_g2s(dst + sp * a_split_bytes + kc * RA * 16,
-                       xp + (((size_t)sp * p.xp_kc + c * UM_KCH + kc) * p.xp_rows + row0) * 16, kc_bytes, &a_full[as]);
-        }
-        if (!A_WARP) break;  // thread 0 joins the epilogue of its (only) tile
+        issue_a_chunks<NSPLIT, AST>(lane, as, aph, nch, a_empty, a_full, sA, a_stage, a_split_bytes, RA, xp, p.xp_kc, p.xp_rows, row0,
+                                    rows_used);
       }
     }
   } else if (warp == W_MMA) {
@@ -333,12 +361,14 @@ __global__ void __launch_bounds__(EW * 32 + 64 + (NBUF == 2 ? 32 : 0), EW == 8 ?
       mbar_wait(&acc_empty[buf], (use & 1) ^ 1);  // the epilogue has drained this buffer (fresh barrier: passes)
       tc_fence_after();
       const uint32_t tm = tmem + (uint32_t)buf * (ACC_COLS * NT);
+      // bulk-copied tiles start at the 8-row boundary below their first row (issue_a_chunks)
+      const uint32_t roff = planes_in ? a_row_off((long long)mtile * (MT * 128) - p.pad_left + UM_PADL) : 0u;
       if (lane == 0 && it < 8) UM_TRACE(16 + it * 4 + 0);
       for (int c = 0; c < nch; ++c) {
         mbar_wait(&a_full[as], aph);
         tc_fence_after();
         if (c == 0 && lane == 0 && it == 0) UM_TRACE(3);
-        const uint64_t a_c = a_desc0 + ((as * a_stage) >> 4);
+        const uint64_t a_c = a_desc0 + ((as * a_stage) >> 4) + roff;
         for (int k0 = 0; k0 < K; k0 += G) {
           mbar_wait(&w_full[ws], wph);
           tc_fence_after();
@@ -390,28 +420,15 @@ __global__ void __launch_bounds__(EW * 32 + 64 + (NBUF == 2 ? 32 : 0), EW == 8 ?
   } else {
     // everything below reads activations written by the previous grid (weights above are static)
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (!A_WARP && planes_in && tid == 0) {
-      // ===================== A by bulk copy from the producer's plane image (one tile per CTA) =====================
-      asm volatile("griddepcontrol.wait;" ::: "memory");  // activations are written by the previous grid
+    if (!A_WARP && planes_in && warp == 0) {
+      // ===================== A by bulk copy from the producer's plane image (one tile per CTA): warp 0, then it joins the epilogue
       const unsigned char* xp = reinterpret_cast<const unsigned char*>(p.xp) + (size_t)b * p.xp_bs;
       // only the rows the taps can reach: MT*128 + (K-1)*dil of the RA rows a stage has room for
-      const uint32_t kc_bytes = (uint32_t)(MT * 128 + (K - 1) * dil) * 16;
-      int as = 0;
-      uint32_t aph = 1;
-      for (int mtile = blockIdx.x; mtile < m_tiles; mtile += gstride) {
-        const long long row0 = (long long)mtile * (MT * 128) - p.pad_left + UM_PADL;
-        for (int c = 0; c < nch; ++c, as = (as + 1 == AST ? 0 : as + 1), aph ^= (as == 0)) {
-          mbar_wait(&a_empty[as], aph);
-          mbar_arrive_expect_tx(&a_full[as], NSPLIT * UM_KCH * kc_bytes);
-          unsigned char* dst = sA + (size_t)as * a_stage;
-          for (int sp = 0; sp < NSPLIT; ++sp)
-#pragma unroll
-            for (int kc = 0; kc < UM_KCH; ++kc)
-              bulk_g2s(dst + sp * a_split_bytes + kc * RA * 16,
-                       xp + (((size_t)sp * p.xp_kc + c * UM_KCH + kc) * p.xp_rows + row0) * 16, kc_bytes, &a_full[as]);
-        }
-        if (!A_WARP) break;  // thread 0 joins the epilogue of its (only) tile
-      }
+      int as_l = 0;
+      uint32_t aph_l = 1;
+      const long long row0 = (long long)blockIdx.x * (MT * 128) - p.pad_left + UM_PADL;
+      issue_a_chunks<NSPLIT, AST>(lane, as_l, aph_l, nch, a_empty, a_full, sA, a_stage, a_split_bytes, RA, xp, p.xp_kc, p.xp_rows, row0,
+                                  MT * 128 + (K - 1) * dil);
     }
     int as = 0;        // gather-mode producer state of the activation ring (runs on across tiles)
     uint32_t aph = 1;

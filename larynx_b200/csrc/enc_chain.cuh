@@ -40,7 +40,8 @@ constexpr uint32_t EA_QPLANE = EA_KC * EA_ROWS * 16;        // 24576
 constexpr uint32_t EA_XPLANE = EA_KC * EA_XR * 16;          // 27648
 constexpr uint32_t EA_PPLANE = (EA_XR / 8) * EA_ROWS * 16;  // 36864
 static_assert(EA_NS * EA_XPLANE + EA_NS * EA_PPLANE <= EC_DATA, "attention operands must fit the conv rings they overlay");
-constexpr size_t EC_SMEM = EC_DATA + 512 + 4 * (64 + 8 * 33 + 128 * 9) + sizeof(EncStep) * EC_MAX_STEPS + 16;
+constexpr size_t EC_SMEM = EC_DATA + 512 + 4 * (64 + 8 * 33 + 3 * 128 * 9 + 4 * 128) + sizeof(EncStep) * EC_MAX_STEPS + 16;
+static_assert(EC_SMEM <= 227 * 1024, "enc_chain: shared memory budget");
 
 // epilogue parameters of conv_umma_epilogue.inc for this kernel (EPI_PLAIN only; register resident)
 struct EncEpiP {
@@ -75,11 +76,6 @@ __device__ __forceinline__ void ec_red_release(unsigned int* p) {
   asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
 }
 __device__ __forceinline__ void ec_epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(EC_EW * 32) : "memory"); }
-__device__ __forceinline__ float ec_ldcg(const float* p) {  // L2-coherent load: data other CTAs wrote in earlier steps
-  float v;
-  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
-  return v;
-}
 
 // CTAs of one utterance that take part in a step (the barrier count)
 __device__ __forceinline__ unsigned int ec_expect(const EncStep& st, unsigned int m_tiles) {
@@ -88,7 +84,7 @@ __device__ __forceinline__ unsigned int ec_expect(const EncStep& st, unsigned in
     for (int i = 0; i < st.n_conv; ++i) n += (unsigned int)(st.conv[i].ntiles * st.conv[i].ksplit);
     return n * m_tiles;
   }
-  if (st.type == ES_REDUCE) return 4u * m_tiles;
+  if (st.type == ES_REDUCE) return (unsigned int)EC_YT * m_tiles;
   return (unsigned int)st.att.n_heads;
 }
 // the conv op of a step that CTA row y works on, or nullptr
@@ -134,15 +130,18 @@ __global__ void __launch_bounds__(EC_THREADS, 1) enc_chain_kernel(const __grid_c
   uint64_t* at_qk = bars + 34;       // attention: Q, K' landed
   uint64_t* at_s = bars + 35;        //            S accumulated (Q, K' dead)
   uint64_t* at_v = bars + 36;        //            V' landed
-  uint64_t* at_p = bars + 37;        //            P' image written (128 arrivals)
+  uint64_t* at_p = bars + 37;        //            P' image written (one arrival per epilogue thread)
   uint64_t* at_o = bars + 38;        //            O accumulated (operands dead: the rings may refill)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 40);
   static_assert(EC_WST <= 12 && EC_AST <= 4, "barrier slots");
   float* s_bias = reinterpret_cast<float*>(bars + 64);  // [64]
   const float *s_inv = nullptr, *s_anb = nullptr, *s_ans = nullptr;  // named by the (dead here) coupling branch of the epilogue text
   float* s_red = s_bias + 64;                           // [8][33] LayerNorm partial sums
-  float* s_relk = s_red + 8 * 33;                       // [128][9] relative-key logits of each query
-  EncStep* s_steps = reinterpret_cast<EncStep*>((reinterpret_cast<uintptr_t>(s_relk + 128 * 9) + 15) & ~(uintptr_t)15);
+  float* s_relk = s_red + 8 * 33;                       // [2][128][9] relative-key logits of each query (a copy per column half)
+  float* s_band = s_relk + 2 * 128 * 9;                 // [128][9] scaled, masked logits on the band |j - i| <= window
+  float* s_mx = s_band + 128 * 9;                       // [2][128] row maximum of each column half
+  float* s_sum = s_mx + 2 * 128;                        // [2][128] row sum of each column half
+  EncStep* s_steps = reinterpret_cast<EncStep*>((reinterpret_cast<uintptr_t>(s_sum + 2 * 128) + 15) & ~(uintptr_t)15);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int mtile = blockIdx.x, y = blockIdx.y;
@@ -170,7 +169,7 @@ __global__ void __launch_bounds__(EC_THREADS, 1) enc_chain_kernel(const __grid_c
     mbar_init(at_qk, 1);
     mbar_init(at_s, 1);
     mbar_init(at_v, 1);
-    mbar_init(at_p, 128);
+    mbar_init(at_p, EW * 32);
     mbar_init(at_o, 1);
     fence_barrier_init();
   }
@@ -221,7 +220,10 @@ __global__ void __launch_bounds__(EC_THREADS, 1) enc_chain_kernel(const __grid_c
     }
   } else if (warp == W_ALOAD) {
     // ===================== activation producer: waits for the previous step of THIS utterance, then bulk-copies ========
-    if (lane == 0) {
+    // The whole warp walks the step table (uniform control flow).  Conv steps: lane 0 issues the few large copies of a stage.
+    // Attention steps: 108 + 72 small copies (one per 8-channel group of a plane) — every lane issues its share (a single
+    // lane needed 13 us for Q and K' alone, profiles/r2a_chain_trace.log).
+    {
       int as = 0;
       uint32_t aph = 1, att_use = 0;
       for (int b = blockIdx.z; b < fp.batch; b += gridDim.z) {
@@ -234,33 +236,44 @@ __global__ void __launch_bounds__(EC_THREADS, 1) enc_chain_kernel(const __grid_c
           if (st.type == ES_CONV) {
             const EncConvOp* op = ec_my_op(st, y);
             if (!op) continue;
-            if (sidx > 0) {
-              ec_wait_step(cnt, sidx - 1, ec_expect(s_steps[sidx - 1], m_tiles), b);
-              asm volatile("fence.proxy.async;" ::: "memory");  // other CTAs' generic-proxy writes -> our async-proxy reads
-            }
-            EC_TRACE(sidx, 0);
             const int ks = (y - op->y0) / op->ntiles;
             const int nch = (op->Cin + UM_BKC - 1) / UM_BKC, per = nch / op->ksplit;
+            if (lane == 0 && sidx > 0) ec_wait_step(cnt, sidx - 1, ec_expect(s_steps[sidx - 1], m_tiles), b);
+            __syncwarp();
+            asm volatile("fence.proxy.async;" ::: "memory");  // (each issuing lane) other CTAs' generic-proxy writes -> our async-proxy reads
+            if (lane == 0) EC_TRACE(sidx, 0);
             const unsigned char* xp = op->xp + (size_t)b * op->xp_bs;
-            const uint32_t kc_bytes = (uint32_t)(128 + (op->K - 1)) * 16;
-            const long long row0 = (long long)t0 - op->pad + UM_PADL;
-            for (int c = ks * per; c < (ks + 1) * per; ++c, as = (as + 1 == EC_AST ? 0 : as + 1), aph ^= (as == 0)) {
-              mbar_wait(&a_empty[as], aph);
-              mbar_arrive_expect_tx(&a_full[as], NSPLIT * UM_KCH * kc_bytes);
-              unsigned char* dst = sA + (size_t)as * a_stage;
-              for (int sp = 0; sp < NSPLIT; ++sp)
-#pragma unroll
-                for (int kc = 0; kc < UM_KCH; ++kc)
-                  bulk_g2s(dst + sp * a_split_bytes + kc * RA * 16,
-                           xp + (((size_t)sp * op->xp_kc + c * UM_KCH + kc) * fp.rows + row0) * 16, kc_bytes, &a_full[as]);
+            // copied from the 8-row (128-byte) boundary below the first row: unaligned bulk copies run ~3x slower
+            const long long row0u = (long long)t0 - op->pad + UM_PADL;
+            const uint32_t roff = a_row_off(row0u);
+            const long long row0 = row0u - roff;
+            const uint32_t kc_bytes = (uint32_t)((128 + (op->K - 1) + (int)roff + 7) & ~7) * 16;
+            // a chunk = 3 planes x 4 channel groups = 12 copies of ~2 KB; one lane needs ~100 ns per copy (6 chunks = 7 us in
+            // the ffn1 / qkv steps of profiles/r2a_chain_trace.log): lanes 0-11 and 12-23 issue two chunks at once
+            static_assert(EC_AST >= 2 && NSPLIT * UM_KCH == 12, "lane -> (stage, copy) mapping");
+            const int q = lane / 12, j = lane - q * 12;
+            for (int c0 = 0; c0 < per; c0 += 2) {
+              const int c = ks * per + c0 + q;
+              int sq = as + q;
+              uint32_t pq = aph;
+              if (sq >= EC_AST) { sq -= EC_AST; pq ^= 1; }
+              if (q < 2 && c0 + q < per) {
+                mbar_wait(&a_empty[sq], pq);
+                if (j == 0) mbar_arrive_expect_tx(&a_full[sq], NSPLIT * UM_KCH * kc_bytes);
+                const int sp = j >> 2, kc = j & 3;
+                bulk_g2s(sA + (size_t)sq * a_stage + sp * a_split_bytes + kc * RA * 16,
+                         xp + (((size_t)sp * op->xp_kc + c * UM_KCH + kc) * fp.rows + row0) * 16, kc_bytes, &a_full[sq]);
+              }
+              as += min(2, per - c0);
+              if (as >= EC_AST) { as -= EC_AST; aph ^= 1; }
+              __syncwarp();
             }
           } else if (st.type == ES_ATTN && att_mine(st)) {
             const EncAttnOp& at = st.att;
-            if (sidx > 0) {
-              ec_wait_step(cnt, sidx - 1, ec_expect(s_steps[sidx - 1], m_tiles), b);
-              asm volatile("fence.proxy.async;" ::: "memory");
-            }
-            EC_TRACE(sidx, 0);
+            if (lane == 0 && sidx > 0) ec_wait_step(cnt, sidx - 1, ec_expect(s_steps[sidx - 1], m_tiles), b);
+            __syncwarp();
+            asm volatile("fence.proxy.async;" ::: "memory");  // (each issuing lane) other CTAs' writes -> our async-proxy reads
+            if (lane == 0) EC_TRACE(sidx, 0);
             const int h = y - at.y0;
             const unsigned char* src = at.qkv_p + (size_t)b * at.qkv_bs;
             const int hk = at.H / 8;  // channel groups per q / k / v block
@@ -272,22 +285,25 @@ __global__ void __launch_bounds__(EC_THREADS, 1) enc_chain_kernel(const __grid_c
             unsigned char* sK = smem_raw + EA_NS * EA_QPLANE;
             unsigned char* sV = smem_raw;
             // phase 1: Q rows [0,128) and K' = [K rows [0,128); Ek rows] (image rows >= len are zero)
-            mbar_arrive_expect_tx(at_qk, EA_NS * (EA_QPLANE + EA_XPLANE));
-            for (int sp = 0; sp < EA_NS; ++sp)
-              for (int kc = 0; kc < EA_KC; ++kc) {
-                bulk_g2s(sQ + sp * EA_QPLANE + kc * EA_ROWS * 16, img(0, sp, kc), EA_ROWS * 16, at_qk);
-                bulk_g2s(sK + sp * EA_XPLANE + kc * EA_XR * 16, img(1, sp, kc), EA_ROWS * 16, at_qk);
-                bulk_g2s(sK + sp * EA_XPLANE + kc * EA_XR * 16 + EA_ROWS * 16, at.relk_img + ((size_t)sp * EA_KC + kc) * 256, 256, at_qk);
-              }
+            if (lane == 0) mbar_arrive_expect_tx(at_qk, EA_NS * (EA_QPLANE + EA_XPLANE));
+            __syncwarp();
+            for (int i = lane; i < EA_NS * EA_KC; i += 32) {
+              const int sp = i / EA_KC, kc = i - sp * EA_KC;
+              bulk_g2s(sQ + sp * EA_QPLANE + kc * EA_ROWS * 16, img(0, sp, kc), EA_ROWS * 16, at_qk);
+              bulk_g2s(sK + sp * EA_XPLANE + kc * EA_XR * 16, img(1, sp, kc), EA_ROWS * 16, at_qk);
+              bulk_g2s(sK + sp * EA_XPLANE + kc * EA_XR * 16 + EA_ROWS * 16, at.relk_img + ((size_t)sp * EA_KC + kc) * 256, 256, at_qk);
+            }
             // phase 2: V' = [V; Ev] over the dead Q / K' bytes, as soon as the S MMAs have retired
             mbar_wait(at_s, att_use & 1);
-            mbar_arrive_expect_tx(at_v, EA_NS * EA_XPLANE);
-            for (int sp = 0; sp < EA_NS; ++sp)
-              for (int kc = 0; kc < EA_KC; ++kc) {
-                bulk_g2s(sV + sp * EA_XPLANE + kc * EA_XR * 16, img(2, sp, kc), EA_ROWS * 16, at_v);
-                bulk_g2s(sV + sp * EA_XPLANE + kc * EA_XR * 16 + EA_ROWS * 16, at.relv_img + ((size_t)sp * EA_KC + kc) * 256, 256, at_v);
-              }
+            if (lane == 0) mbar_arrive_expect_tx(at_v, EA_NS * EA_XPLANE);
+            __syncwarp();
+            for (int i = lane; i < EA_NS * EA_KC; i += 32) {
+              const int sp = i / EA_KC, kc = i - sp * EA_KC;
+              bulk_g2s(sV + sp * EA_XPLANE + kc * EA_XR * 16, img(2, sp, kc), EA_ROWS * 16, at_v);
+              bulk_g2s(sV + sp * EA_XPLANE + kc * EA_XR * 16 + EA_ROWS * 16, at.relv_img + ((size_t)sp * EA_KC + kc) * 256, 256, at_v);
+            }
             ++att_use;
+            __syncwarp();
           }
         }
       }
@@ -311,6 +327,7 @@ __global__ void __launch_bounds__(EC_THREADS, 1) enc_chain_kernel(const __grid_c
           const uint32_t idesc3 = make_idesc_bf16_f32(128, 3 * NT);
           const uint64_t b_desc0 = make_smem_desc(smem_u32(sW), NSPLIT * NT * 16, 128);
           const uint32_t b_ks = (2 * NSPLIT * NT * 16) >> 4;
+          const uint32_t roff = a_row_off((long long)t0 - op->pad + UM_PADL);
           mbar_wait(acc_empty, (use & 1) ^ 1);  // the epilogue of this CTA's previous conv step has drained the accumulator
           tc_fence_after();
           const uint32_t w_stage = (uint32_t)NSPLIT * UM_KCH * NT * 16;
@@ -328,7 +345,7 @@ __global__ void __launch_bounds__(EC_THREADS, 1) enc_chain_kernel(const __grid_c
                 if (i == 0 && lane == 0) EC_TRACE(sidx, 1);
               }
               if (elect_one()) {
-                const uint64_t a_k = a_desc0 + ((as * a_stage) >> 4) + (uint32_t)k;  // conv tap (dilation 1): shift by k rows
+                const uint64_t a_k = a_desc0 + ((as * a_stage) >> 4) + roff + (uint32_t)k;  // conv tap (dilation 1): shift by k rows
                 const uint64_t b_k = b_desc0 + ((ws * w_slot + j * w_stage) >> 4);
 #pragma unroll
                 for (int ks2 = 0; ks2 < UM_BKC / 16; ++ks2) {
@@ -444,79 +461,89 @@ __global__ void __launch_bounds__(EC_THREADS, 1) enc_chain_kernel(const __grid_c
           if (lane == 0) mbar_arrive(acc_empty);
           ++use;
         } else if (st.type == ES_REDUCE) {
-          if (y >= 4) continue;
+          // all EC_YT CTA rows of the time tile take 128 / EC_YT = 8 rows each: one 8-channel group per thread, so every
+          // thread has ONE batch of independent L2 loads in flight (4 CTAs x 4 groups per thread took 8-12 us per step)
           took_part = true;
           const EncReduceOp& r = st.red;
           if (tid == 0 && sidx > 0) ec_wait_step(cnt, sidx - 1, ec_expect(s_steps[sidx - 1], m_tiles), b);
           ec_epi_bar();
           if (tid == 0) EC_TRACE(sidx, 4);
-          // 32 time steps x 8 channel-group sets; each thread keeps its C/8/8 groups of 8 channels in registers
-          const int tx = tid & 31, ty = tid >> 5;
-          const int t = t0 + y * 32 + tx;
+          constexpr int RPC = 128 / EC_YT;  // rows per CTA
+          static_assert(RPC == 8 && EW * 32 == 256, "reduce mapping: 8 rows x 32 channel groups per CTA");
+          const int tx = tid & 7, g = tid >> 3;  // row, 8-channel group (a warp = 4 groups x 8 rows)
+          const int t = t0 + y * RPC + tx;
           const bool valid = t < Lb;
           const int ngrp = r.C >> 3;
+          const bool ok = valid && g < ngrp;
           const float* xb = r.x + (size_t)b * r.x_bs;
           const float* rb = r.res ? r.res + (size_t)b * r.res_bs : nullptr;
-          float v[4][8];
+          float v[8];
           float sum = 0.f;
+          {
+            // plain L2 loads (ld.global.cg: the partials and the residual were written by other CTAs in earlier steps), all
+            // independent and issued back to back
+            float part[4][8], rs[8];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int g = ty + i * 8;
+            for (int e = 0; e < 8; ++e) {
+              const size_t off = ok ? (size_t)(g * 8 + e) * r.ld + t : 0;
+#pragma unroll
+              for (int pp = 0; pp < 4; ++pp) part[pp][e] = pp < r.parts ? __ldcg(xb + (size_t)pp * r.part_stride + off) : 0.f;
+              rs[e] = rb ? __ldcg(rb + off) : 0.f;
+            }
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               const int c = g * 8 + e;
-              const bool ok = valid && g < ngrp;  // branch-free: all loads of the column are in flight together
-              const size_t off = ok ? (size_t)c * r.ld + t : 0;
-              float a = ec_ldcg(xb + off);
-              for (int pp = 1; pp < r.parts; ++pp) a += ec_ldcg(xb + (size_t)pp * r.part_stride + off);
+              float a = part[0][e];
+#pragma unroll
+              for (int pp = 1; pp < 4; ++pp)
+                if (pp < r.parts) a += part[pp][e];
               if (r.bias) a += r.bias[ok ? c : 0];
-              if (rb) a += ec_ldcg(rb + off);
+              if (rb) a += rs[e];
               if (r.pre_relu) a = fmaxf(a, 0.f);
               a = ok ? a : 0.f;
-              v[i][e] = a;
+              v[e] = a;
               sum += a;
             }
           }
           float mean = 0.f, rstd = 1.f;
           if (r.gamma) {
-            s_red[ty * 33 + tx] = sum;
+            // row statistics: 4 groups of a row inside the warp (lanes tx, tx+8, tx+16, tx+24), then the 8 warps through smem
+            sum += __shfl_xor_sync(0xffffffffu, sum, 8);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+            if (lane < 8) s_red[warp * 8 + lane] = sum;
             ec_epi_bar();
             float tot = 0.f;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) tot += s_red[j * 33 + tx];
+            for (int j = 0; j < 8; ++j) tot += s_red[j * 8 + tx];
             mean = tot / (float)r.C;
-            ec_epi_bar();
             float q = 0.f;
+            if (g < ngrp) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              if (ty + i * 8 < ngrp) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  const float d = v[i][e] - mean;
-                  q += d * d;
-                }
+              for (int e = 0; e < 8; ++e) {
+                const float d = v[e] - mean;
+                q += d * d;
               }
             }
-            s_red[ty * 33 + tx] = q;
+            q += __shfl_xor_sync(0xffffffffu, q, 8);
+            q += __shfl_xor_sync(0xffffffffu, q, 16);
+            ec_epi_bar();  // every thread has read the sums
+            if (lane < 8) s_red[warp * 8 + lane] = q;
             ec_epi_bar();
             float qt = 0.f;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) qt += s_red[j * 33 + tx];
+            for (int j = 0; j < 8; ++j) qt += s_red[j * 8 + tx];
             rstd = rsqrtf(qt / (float)r.C + 1e-4f);
           }
           float* yb = r.y ? r.y + (size_t)b * r.y_bs : nullptr;
           unsigned char* pb = r.yp ? r.yp + (size_t)b * r.yp_bs : nullptr;
           const size_t pstride = (size_t)r.yp_kc * fp.rows * 16;
           const uint4 z4 = make_uint4(0, 0, 0, 0);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int g = ty + i * 8;
-            if (g >= ngrp) continue;
+          if (g < ngrp) {
             float o[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               const int c = g * 8 + e;
-              float w = v[i][e];
+              float w = v[e];
               if (r.gamma) w = (w - mean) * rstd * r.gamma[c] + r.beta[c];
               if (r.post_relu) w = fmaxf(w, 0.f);
               o[e] = valid ? w : 0.f;
@@ -529,9 +556,9 @@ __global__ void __launch_bounds__(EC_THREADS, 1) enc_chain_kernel(const __grid_c
               *reinterpret_cast<uint4*>(base) = q3[0];
               *reinterpret_cast<uint4*>(base + pstride) = q3[1];
               *reinterpret_cast<uint4*>(base + 2 * pstride) = q3[2];
-              // zero rows: t in [-PADL, 0) by the first row block; the 128 rows behind the last tile, 32 per row block
+              // zero rows: t in [-PADL, 0) by the first row block; the 128 rows behind the last tile, 8 per row block
               if (mtile == 0 && y == 0) {
-                for (int rr = tx; rr < UM_PADL; rr += 32) {
+                for (int rr = tx; rr < UM_PADL; rr += RPC) {
                   unsigned char* zb = pb + ((size_t)g * fp.rows + rr) * 16;
                   *reinterpret_cast<uint4*>(zb) = z4;
                   *reinterpret_cast<uint4*>(zb + pstride) = z4;
@@ -539,7 +566,7 @@ __global__ void __launch_bounds__(EC_THREADS, 1) enc_chain_kernel(const __grid_c
                 }
               }
               if (t0 + 128 >= Lb) {
-                unsigned char* zb = pb + ((size_t)g * fp.rows + UM_PADL + t0 + 128 + y * 32 + tx) * 16;
+                unsigned char* zb = pb + ((size_t)g * fp.rows + UM_PADL + t0 + 128 + y * RPC + tx) * 16;
                 *reinterpret_cast<uint4*>(zb) = z4;
                 *reinterpret_cast<uint4*>(zb + pstride) = z4;
                 *reinterpret_cast<uint4*>(zb + 2 * pstride) = z4;
@@ -553,128 +580,137 @@ __global__ void __launch_bounds__(EC_THREADS, 1) enc_chain_kernel(const __grid_c
           const int h = y - at.y0;
           const int nrel = 2 * at.window + 1;
           unsigned char* sP = smem_raw + EA_NS * EA_XPLANE;
-          if (warp < 4) {
-            // ---- softmax + epilogue: thread = query row = TMEM lane (attn_umma.cu)
-            const int i = tid;  // 0..127
-            const bool row_ok = i < Lb;
-            const float inv_sqrt = 1.f / sqrtf((float)EA_DK);
-            float* my_relk = s_relk + i * 9;
-            mbar_wait(at_s, att_use & 1);
-            tc_fence_after();
-            if (tid == 0) EC_TRACE(sidx, 4);
-            const uint32_t lane_addr = ((uint32_t)(warp * 32) << 16);
-            {
-              uint32_t raw[32];
-              tmem_ld32(tS + lane_addr + EA_ROWS, raw);  // columns 128..159: q_i . Ek[r] in the first 2w+1
-              tmem_ld_wait();
+          // ---- softmax + epilogue on all 8 warps: thread = (query row = TMEM lane, column half).  Warps w and w + 4 read the
+          // same 32 lanes; `half` picks the 64 key columns (softmax) / 48 output channels (epilogue) a thread owns.  One
+          // thread per row (the first version) spent ~6k dependent instructions on a single warp per scheduler: 56 us.
+          const int i = (warp & 3) * 32 + lane;  // 0..127
+          const int half = warp >> 2;
+          const bool row_ok = i < Lb;
+          const float inv_sqrt = 1.f / sqrtf((float)EA_DK);
+          float* my_relk = s_relk + (half * 128 + i) * 9;
+          float* my_band = s_band + i * 9;
+          mbar_wait(at_s, att_use & 1);
+          tc_fence_after();
+          if (tid == 0) EC_TRACE(sidx, 4);
+          const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32) << 16);
+          {
+            uint32_t raw[32];
+            tmem_ld32(tS + lane_addr + EA_ROWS, raw);  // columns 128..159: q_i . Ek[r] in the first 2w+1
+            tmem_ld_wait();
 #pragma unroll
-              for (int rr = 0; rr < 9; ++rr) my_relk[rr] = __uint_as_float(raw[rr]);
+            for (int rr = 0; rr < 9; ++rr) my_relk[rr] = __uint_as_float(raw[rr]);
+          }
+          constexpr int HC = EA_ROWS / 2;  // key columns per thread
+          float srow[HC];
+          float mx = -INFINITY;
+#pragma unroll
+          for (int g = 0; g < HC / 32; ++g) {
+            uint32_t raw[32];
+            tmem_ld32(tS + lane_addr + half * HC + g * 32, raw);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int col = half * HC + g * 32 + j;
+              float sv = __uint_as_float(raw[j]);
+              const int rr = col - i + at.window;
+              const bool in_band = (unsigned)rr < (unsigned)nrel;
+              if (in_band) sv += my_relk[rr];
+              sv *= inv_sqrt;
+              sv = col < Lb ? sv : -INFINITY;
+              if (in_band) my_band[rr] = sv;  // the band probabilities are rebuilt from these (no dynamic register index)
+              srow[g * 32 + j] = sv;
+              mx = fmaxf(mx, sv);
             }
-            float srow[EA_ROWS];
-            float mx = -INFINITY;
+          }
+          s_mx[half * 128 + i] = mx;
+          ec_epi_bar();
+          mx = fmaxf(s_mx[i], s_mx[128 + i]);
+          float ssum = 0.f;
 #pragma unroll
-            for (int g = 0; g < EA_ROWS / 32; ++g) {
-              uint32_t raw[32];
-              tmem_ld32(tS + lane_addr + g * 32, raw);
-              tmem_ld_wait();
+          for (int c2 = 0; c2 < HC; ++c2) {
+            const int col = half * HC + c2;
+            const float e = col < Lb ? __expf(srow[c2] - mx) : 0.f;
+            srow[c2] = e;
+            ssum += e;
+          }
+          s_sum[half * 128 + i] = ssum;
+          ec_epi_bar();
+          ssum = s_sum[i] + s_sum[128 + i];
+          const float inv = row_ok ? 1.f / ssum : 0.f;
+          // P' image over the dead K' bytes (the S MMAs have retired: at_s)
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const int col = g * 32 + j;
-                float sv = __uint_as_float(raw[j]);
-                const int rr = col - i + at.window;
-                if (rr >= 0 && rr < nrel) sv += my_relk[rr];
-                sv *= inv_sqrt;
-                sv = col < Lb ? sv : -INFINITY;
-                srow[col] = sv;
-                mx = fmaxf(mx, sv);
-              }
-            }
-            float ssum = 0.f;
+          for (int q8 = 0; q8 < HC / 8; ++q8) {
+            const int kc = half * (HC / 8) + q8;
+            float v8[8];
 #pragma unroll
-            for (int col = 0; col < EA_ROWS; ++col) {
-              const float e = col < Lb ? __expf(srow[col] - mx) : 0.f;
-              srow[col] = e;
-              ssum += e;
-            }
-            const float inv = row_ok ? 1.f / ssum : 0.f;
-            // P' image over the dead K' bytes (the S MMAs have retired: at_s)
-            float band[16];
+            for (int e = 0; e < 8; ++e) v8[e] = srow[q8 * 8 + e] * inv;
+            uint4 q3[3];
+            split8<3>(v8, q3);
+            unsigned char* o = sP + ((size_t)kc * EA_ROWS + i) * 16;
+            *reinterpret_cast<uint4*>(o) = q3[0];
+            *reinterpret_cast<uint4*>(o + EA_PPLANE) = q3[1];
+            *reinterpret_cast<uint4*>(o + 2 * EA_PPLANE) = q3[2];
+          }
+          // band probabilities p[i][i + r - w] as 16 extra "keys" (they meet the Ev rows of V'): half 0 writes r = 0..7,
+          // half 1 writes r = 8 and the zero padding
+          {
+            float band[8];
 #pragma unroll
-            for (int rr = 0; rr < 16; ++rr) band[rr] = 0.f;
-#pragma unroll
-            for (int kc = 0; kc < EA_ROWS / 8; ++kc) {
-              float v8[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v8[e] = srow[kc * 8 + e] * inv;
-              uint4 q3[3];
-              split8<3>(v8, q3);
-              unsigned char* o = sP + ((size_t)kc * EA_ROWS + i) * 16;
-              *reinterpret_cast<uint4*>(o) = q3[0];
-              *reinterpret_cast<uint4*>(o + EA_PPLANE) = q3[1];
-              *reinterpret_cast<uint4*>(o + 2 * EA_PPLANE) = q3[2];
-            }
-            // band probabilities p[i][i + r - w] as 16 extra "keys" (they meet the Ev rows of V')
-#pragma unroll
-            for (int rr = 0; rr < 9; ++rr) {
+            for (int e = 0; e < 8; ++e) {
+              const int rr = half * 8 + e;
               const int col = i + rr - at.window;
               float pv = 0.f;
-              if (rr < nrel && col >= 0 && col < Lb) {
-                float sv = 0.f;
-#pragma unroll
-                for (int c2 = 0; c2 < EA_ROWS; ++c2) sv = c2 == col ? srow[c2] : sv;  // register select, no local memory
-                pv = sv * inv;
-              }
-              band[rr] = pv;
+              if (rr < nrel && col >= 0 && col < Lb) pv = __expf(my_band[rr < 9 ? rr : 0] - mx) * inv;
+              band[e] = pv;
             }
-#pragma unroll
-            for (int kc = 0; kc < 2; ++kc) {
-              uint4 q3[3];
-              split8<3>(band + kc * 8, q3);
-              unsigned char* o = sP + ((size_t)(EA_ROWS / 8 + kc) * EA_ROWS + i) * 16;
-              *reinterpret_cast<uint4*>(o) = q3[0];
-              *reinterpret_cast<uint4*>(o + EA_PPLANE) = q3[1];
-              *reinterpret_cast<uint4*>(o + 2 * EA_PPLANE) = q3[2];
-            }
-            fence_proxy_async_smem();
-            mbar_arrive(at_p);
-
-            mbar_wait(at_o, att_use & 1);
-            tc_fence_after();
-            unsigned char* opb = at.out_p + (size_t)b * at.out_bs;
-            const size_t ostride = (size_t)at.out_kc * fp.rows * 16;
-#pragma unroll
-            for (int g = 0; g < EA_DK / 32; ++g) {
-              uint32_t raw[32];
-              tmem_ld32(tO + lane_addr + g * 32, raw);
-              tmem_ld_wait();
-              float o[32];
-#pragma unroll
-              for (int j = 0; j < 32; ++j) o[j] = row_ok ? __uint_as_float(raw[j]) : 0.f;
-#pragma unroll
-              for (int q4 = 0; q4 < 4; ++q4) {
-                uint4 q3[3];
-                split8<3>(o + q4 * 8, q3);
-                const int kc = h * EA_KC + g * 4 + q4;
-                unsigned char* dst = opb + ((size_t)kc * fp.rows + UM_PADL + i) * 16;
-                *reinterpret_cast<uint4*>(dst) = q3[0];
-                *reinterpret_cast<uint4*>(dst + ostride) = q3[1];
-                *reinterpret_cast<uint4*>(dst + 2 * ostride) = q3[2];
-                // zero rows around the data: t in [-PADL, 0) by rows i < PADL, t in [128, 256) by all rows
-                const uint4 z = make_uint4(0, 0, 0, 0);
-                if (i < UM_PADL) {
-                  unsigned char* zf = opb + ((size_t)kc * fp.rows + i) * 16;
-                  *reinterpret_cast<uint4*>(zf) = z;
-                  *reinterpret_cast<uint4*>(zf + ostride) = z;
-                  *reinterpret_cast<uint4*>(zf + 2 * ostride) = z;
-                }
-                unsigned char* zt = opb + ((size_t)kc * fp.rows + UM_PADL + EA_ROWS + i) * 16;
-                *reinterpret_cast<uint4*>(zt) = z;
-                *reinterpret_cast<uint4*>(zt + ostride) = z;
-                *reinterpret_cast<uint4*>(zt + 2 * ostride) = z;
-              }
-            }
-            tc_fence_before();
+            uint4 q3[3];
+            split8<3>(band, q3);
+            unsigned char* o = sP + ((size_t)(EA_ROWS / 8 + half) * EA_ROWS + i) * 16;
+            *reinterpret_cast<uint4*>(o) = q3[0];
+            *reinterpret_cast<uint4*>(o + EA_PPLANE) = q3[1];
+            *reinterpret_cast<uint4*>(o + 2 * EA_PPLANE) = q3[2];
           }
+          fence_proxy_async_smem();
+          mbar_arrive(at_p);
+
+          mbar_wait(at_o, att_use & 1);
+          tc_fence_after();
+          unsigned char* opb = at.out_p + (size_t)b * at.out_bs;
+          const size_t ostride = (size_t)at.out_kc * fp.rows * 16;
+          // output channels [48*half, 48*half + 48) of this head: three 16-column pieces
+#pragma unroll
+          for (int g = 0; g < 3; ++g) {
+            const int c0 = half * (EA_DK / 2) + g * 16;
+            uint32_t raw[16];
+            tmem_ld16(tO + lane_addr + c0, raw);
+            tmem_ld_wait();
+            float o[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] = row_ok ? __uint_as_float(raw[j]) : 0.f;
+#pragma unroll
+            for (int q4 = 0; q4 < 2; ++q4) {
+              uint4 q3[3];
+              split8<3>(o + q4 * 8, q3);
+              const int kc = h * EA_KC + c0 / 8 + q4;
+              unsigned char* dst = opb + ((size_t)kc * fp.rows + UM_PADL + i) * 16;
+              *reinterpret_cast<uint4*>(dst) = q3[0];
+              *reinterpret_cast<uint4*>(dst + ostride) = q3[1];
+              *reinterpret_cast<uint4*>(dst + 2 * ostride) = q3[2];
+              // zero rows around the data: t in [-PADL, 0) by rows i < PADL, t in [128, 256) by all rows
+              const uint4 z = make_uint4(0, 0, 0, 0);
+              if (i < UM_PADL) {
+                unsigned char* zf = opb + ((size_t)kc * fp.rows + i) * 16;
+                *reinterpret_cast<uint4*>(zf) = z;
+                *reinterpret_cast<uint4*>(zf + ostride) = z;
+                *reinterpret_cast<uint4*>(zf + 2 * ostride) = z;
+              }
+              unsigned char* zt = opb + ((size_t)kc * fp.rows + UM_PADL + EA_ROWS + i) * 16;
+              *reinterpret_cast<uint4*>(zt) = z;
+              *reinterpret_cast<uint4*>(zt + ostride) = z;
+              *reinterpret_cast<uint4*>(zt + 2 * ostride) = z;
+            }
+          }
+          tc_fence_before();
           ++att_use;
         }
         if (!took_part) continue;

@@ -26,7 +26,7 @@ struct EncConvOp {
 };
 
 // Sum of K-split partials (+ bias, + residual) followed by the channel LayerNorm (glow_tts/layers.py:19-28), or just the
-// sum when gamma == nullptr.  Rows are split 32 per CTA over CTA rows y < 4 of each time tile.
+// sum when gamma == nullptr.  Rows are split 128 / EC_YT = 8 per CTA over all CTA rows of each time tile.
 struct EncReduceOp {
   const float* x;        // [parts][batch][C][ld]
   long long x_bs, part_stride;

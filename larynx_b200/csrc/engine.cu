@@ -279,7 +279,8 @@ struct Planes {
   long long bs = 0;  // bytes per batch item
   int kc = 0, rows = 0, nsplit = 2;
 };
-static int plane_rows(int Lin_max, int u) { return 40 + (Lin_max + 511) / 512 * 512 * u + 256; }  // whole 512-row tiles + tail
+// whole 512-row tiles + tail (the fused ResBlock kernel's last tile window reaches up to ~1100 rows past the end: rbpair_umma.cu)
+static int plane_rows(int Lin_max, int u) { return 40 + (Lin_max + 511) / 512 * 512 * u + 1280; }
 static size_t plane_item_bytes(int channels, int rows, int nsplit) { return (size_t)nsplit * ((channels + 31) / 32 * 4) * rows * 16; }
 static Planes take_planes(Arena& a, int batch, int channels, int rows, int nsplit) {
   Planes pl;
@@ -304,6 +305,7 @@ static void set_out(ConvParams& p, const Planes& pl, float slope, const Planes* 
 //   attn_simt     SIMT attention only
 //   no_flow_chain flow decoder as one launch per conv instead of the persistent kernel (flow_chain.cuh)
 //   no_enc_chain  text encoder as one launch per layer instead of the persistent kernel (enc_chain.cuh)
+//   no_rbpair     HiFi-GAN ResBlock convs of the narrow stages as two launches instead of the fused kernel (rbpair_umma.cuh)
 //   chain_trace   per-layer phase stamps of the persistent kernels on stderr
 //   trace         per-conv %globaltimer phase trace on stderr (single-threaded use; implies no_flow_chain)
 static bool dbg_flag(const char* name) {
@@ -1212,19 +1214,41 @@ static void hifigan_run(const b200tts_hifigan* m, b200tts_call* c, const float* 
                            !conv_trace();
       if (umma_rb) {
         const int ndil = m->rb[i * nk].ndil;
+        static const bool no_pair = dbg_flag("no_rbpair");
         for (int d = 0; d < ndil; ++d) {
-          ConvParams ps[3];
+          ConvParams ps[3], qs[3];
           bool pl[3];
           for (int j = 0; j < 3; ++j) {
             fill_c1(j, d, ps[j], pl[j]);
             bind(ps[j], m->rb[i * nk + j].c1[d]);
+            fill_c2(j, d, qs[j], pl[j]);
+            bind(qs[j], m->rb[i * nk + j].c2[d]);
           }
-          c->launches += launch_conv_umma_batch(ps, 3, batch, L, s);
-          for (int j = 0; j < 3; ++j) {
-            fill_c2(j, d, ps[j], pl[j]);
-            bind(ps[j], m->rb[i * nk + j].c2[d]);
+          // narrow stages: c1 -> c2 fused, T stays in shared memory (rbpair_umma.cuh).  Its tiles overlap, so a step must not
+          // rewrite the image it reads: x ping-pongs U -> R -> T(free in this mode) -> fp32 R.
+          ConvParams f1[3], f2[3];
+          bool fused = !no_pair && pl[0] && pl[1] && pl[2] && 3 * batch <= 148;
+          if (fused) {
+            for (int j = 0; j < 3; ++j) {
+              const Planes& in = d == 0 ? U_p : ((d & 1) ? R_p[j] : T_p[j]);
+              const Planes& out = (d & 1) ? T_p[j] : R_p[j];
+              f1[j] = ps[j];
+              f2[j] = qs[j];
+              set_in(f1[j], in);
+              f1[j].yp = nullptr;
+              f1[j].yp_slope = 0.1f;  // T = leaky_relu(c1(.), 0.1), kept on the SM
+              f2[j].xp = nullptr;
+              f2[j].rp = in.ptr; f2[j].rp_bs = in.bs; f2[j].rp_kc = in.kc; f2[j].rp_rows = in.rows; f2[j].rp_inv_slope = 10.f;
+              if (d + 1 < ndil) set_out(f2[j], out, 0.1f);
+            }
+            fused = rbpair_umma_supported(f1, f2, 3);
           }
-          c->launches += launch_conv_umma_batch(ps, 3, batch, L, s);
+          if (fused) {
+            c->launches += launch_rbpair_umma(f1, f2, 3, batch, L, s);
+          } else {
+            c->launches += launch_conv_umma_batch(ps, 3, batch, L, s);
+            c->launches += launch_conv_umma_batch(qs, 3, batch, L, s);
+          }
         }
       } else {
         for (int j = 0; j < nk; ++j) {
@@ -1494,6 +1518,7 @@ int b200tts_call_create(int device, b200tts_call** out) {
   B2_CUDA(cudaSetDevice(device));
   conv1d_init_attributes();
   conv_umma_init_attributes();
+  rbpair_umma_init_attributes();
   attention_init_attributes();
   attn_umma_init_attributes();
   flow_chain_init_attributes();

@@ -225,9 +225,13 @@ __global__ void __launch_bounds__(FC_THREADS, 1) flow_chain_kernel(const __grid_
     }
   } else if (warp == W_ALOAD) {
     // ===================== activation producer: waits for the previous layer of THIS utterance, then bulk-copies ========
-    if (lane == 0) {
+    // The whole warp walks the layers; a 32-channel chunk is 2 planes x 4 channel groups = 8 copies of ~2 KB, and one lane
+    // needs ~100 ns per copy (48 copies per layer = most of the 4.6-5.3 us "mma" phase in profiles/r2a_chain_trace.log), so
+    // the copies of up to four chunks (= the four ring stages) are issued by 32 lanes at once.
+    {
       int as = 0;
       uint32_t aph = 1;
+      const int q = lane >> 3, j = lane & 7;
       for (int b = blockIdx.z; b < fp.batch; b += gridDim.z) {
         const int Lb = fp.lens[b];
         if (t0 >= Lb) continue;
@@ -239,7 +243,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) flow_chain_kernel(const __grid_
             const FlowStep st = flow_step(fp, step, y);
             const int L = blk * n_steps + step;
             if (st.active) {
-              if (L > 0) {
+              if (L > 0 && lane == 0) {
                 // every CTA of this utterance has finished (and published) layer L-1 — and with it, in order, all earlier ones
                 unsigned int spins = 0;
                 while (fc_ld_acquire(cnt + (L - 1)) < prev_expect) {
@@ -248,9 +252,10 @@ __global__ void __launch_bounds__(FC_THREADS, 1) flow_chain_kernel(const __grid_
                     __trap();
                   }
                 }
-                asm volatile("fence.proxy.async;" ::: "memory");  // other CTAs' generic-proxy writes -> our async-proxy reads
               }
-              FC_TRACE(L, 0);
+              __syncwarp();
+              asm volatile("fence.proxy.async;" ::: "memory");  // (each issuing lane) other CTAs' generic-proxy writes -> our async-proxy reads
+              if (lane == 0) FC_TRACE(L, 0);
               const unsigned char* img;
               long long bs;
               int kc_total;
@@ -259,17 +264,27 @@ __global__ void __launch_bounds__(FC_THREADS, 1) flow_chain_kernel(const __grid_
               else if (st.kind == FS_END) { img = fp.K_p; bs = fp.Hp_bs; kc_total = fp.Hp_kc; }
               else { img = fp.A_p; bs = fp.Hp_bs; kc_total = fp.Hp_kc; }
               const unsigned char* xp = img + (size_t)b * bs;
-              const uint32_t kc_bytes = (uint32_t)(128 + (st.K - 1) * st.dil) * 16;
-              const long long row0 = (long long)t0 - st.pad + UM_PADL;
-              for (int c = 0; c < st.nch; ++c, as = (as + 1 == FC_AST ? 0 : as + 1), aph ^= (as == 0)) {
-                mbar_wait(&a_empty[as], aph);
-                mbar_arrive_expect_tx(&a_full[as], NSPLIT * UM_KCH * kc_bytes);
-                unsigned char* dst = sA + (size_t)as * a_stage;
-                for (int sp = 0; sp < NSPLIT; ++sp)
-#pragma unroll
-                  for (int kc = 0; kc < UM_KCH; ++kc)
-                    bulk_g2s(dst + sp * a_split_bytes + kc * RA * 16,
-                             xp + (((size_t)sp * kc_total + c * UM_KCH + kc) * fp.rows + row0) * 16, kc_bytes, &a_full[as]);
+              // copied from the 8-row (128-byte) boundary below the first row: unaligned bulk copies run ~3x slower
+              const long long row0u = (long long)t0 - st.pad + UM_PADL;
+              const uint32_t roff = a_row_off(row0u);
+              const long long row0 = row0u - roff;
+              const uint32_t kc_bytes = (uint32_t)((128 + (st.K - 1) * st.dil + (int)roff + 7) & ~7) * 16;
+              static_assert(FC_AST == 4 && NSPLIT * UM_KCH == 8, "lane -> (stage, copy) mapping");
+              for (int c0 = 0; c0 < st.nch; c0 += FC_AST) {
+                const int c = c0 + q;
+                int sq = as + q;
+                uint32_t pq = aph;
+                if (sq >= FC_AST) { sq -= FC_AST; pq ^= 1; }
+                if (c < st.nch) {
+                  mbar_wait(&a_empty[sq], pq);
+                  if (j == 0) mbar_arrive_expect_tx(&a_full[sq], NSPLIT * UM_KCH * kc_bytes);
+                  const int sp = j >> 2, kc = j & 3;
+                  bulk_g2s(sA + (size_t)sq * a_stage + sp * a_split_bytes + kc * RA * 16,
+                           xp + (((size_t)sp * kc_total + c * UM_KCH + kc) * fp.rows + row0) * 16, kc_bytes, &a_full[sq]);
+                }
+                as += min(FC_AST, st.nch - c0);
+                if (as >= FC_AST) { as -= FC_AST; aph ^= 1; }
+                __syncwarp();
               }
             }
             prev_expect = (unsigned int)st.n_active * m_tiles;
@@ -294,6 +309,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) flow_chain_kernel(const __grid_
           const uint64_t b_desc0 = make_smem_desc(smem_u32(sW), NSPLIT * NT * 16, 128);
           const uint32_t b_ks = (2 * NSPLIT * NT * 16) >> 4;
           const uint32_t tm = tmem + (st.acc ? 128u : 0u);
+          const uint32_t roff = a_row_off((long long)t0 - st.pad + UM_PADL);
           mbar_wait(acc_empty, (use & 1) ^ 1);  // the epilogue of this CTA's previous step is done with the accumulators
           tc_fence_after();
           const uint32_t w_stage = (uint32_t)NSPLIT * UM_KCH * NT * 16;
@@ -315,7 +331,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) flow_chain_kernel(const __grid_
               tc_fence_after();
               if (c == 0 && lane == 0) FC_TRACE(blk * n_steps + step, 2);
               if (elect_one()) {
-                const uint64_t a_c = a_desc0 + ((as * a_stage) >> 4);
+                const uint64_t a_c = a_desc0 + ((as * a_stage) >> 4) + roff;
                 for (int k = 0; k < K; ++k)
                   issue(a_c + (uint32_t)(k * dil), b_desc0 + ((ws * w_slot + k * w_stage) >> 4), (c == 0 && k == 0 && st.init) ? 0u : 1u);
                 mma_commit(&w_empty[ws]);
@@ -336,7 +352,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) flow_chain_kernel(const __grid_
                 tc_fence_after();
                 if (c0 + j == 0 && lane == 0) FC_TRACE(blk * n_steps + step, 1);
                 if (elect_one()) {
-                  issue(a_desc0 + ((as * a_stage) >> 4), b_desc0 + ((ws * w_slot + j * w_stage) >> 4), (c0 + j == 0 && st.init) ? 0u : 1u);
+                  issue(a_desc0 + ((as * a_stage) >> 4) + roff, b_desc0 + ((ws * w_slot + j * w_stage) >> 4), (c0 + j == 0 && st.init) ? 0u : 1u);
                   mma_commit(&a_empty[as]);
                   if (j == cnt - 1) mma_commit(&w_empty[ws]);
                 }

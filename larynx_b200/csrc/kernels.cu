@@ -378,8 +378,18 @@ __global__ void __launch_bounds__(256) duration_kernel(const float* __restrict__
     int wc = 0;
     float lw = 0.f;
     if (t < len) {
+      // the fma chain keeps the channel order (bit-identical results); the loads of 32 channels are issued together
+      // (one dependent L2 round trip per channel made this 1-CTA kernel 53 us long)
       float a = 0.f;
-      for (int c = 0; c < C; ++c) a = fmaf(pw[c], hb[(size_t)c * h_ld + t], a);
+      int c0 = 0;
+      for (; c0 + 32 <= C; c0 += 32) {
+        float x[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = __ldcg(hb + (size_t)(c0 + j) * h_ld + t);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) a = fmaf(pw[c0 + j], x[j], a);
+      }
+      for (int c = c0; c < C; ++c) a = fmaf(pw[c], hb[(size_t)c * h_ld + t], a);
       lw = a + pb[0];
       const float w = expf(lw) * length_scale;
       wc = (int)ceilf(w);

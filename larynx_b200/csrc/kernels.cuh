@@ -10,6 +10,10 @@ void conv1d_init_attributes();
 int launch_conv_umma(const ConvParams& p, int batch, int Lmax, cudaStream_t stream);
 int launch_conv_umma_batch(const ConvParams* ps, int n, int batch, int Lmax, cudaStream_t stream);
 void conv_umma_init_attributes();
+// one ResBlock1 step (c1 -> LeakyReLU -> c2 + residual) per launch, T kept in shared memory (rbpair_umma.cu)
+void rbpair_umma_init_attributes();
+bool rbpair_umma_supported(const ConvParams* c1, const ConvParams* c2, int n);
+int launch_rbpair_umma(const ConvParams* c1, const ConvParams* c2, int n, int batch, int Lmax, cudaStream_t stream);
 void attention_init_attributes();
 void attn_umma_init_attributes();
 bool attn_umma_supported(int H, int n_heads, int window, int Tmax);

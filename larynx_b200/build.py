@@ -15,7 +15,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libb200tts.so"
-SOURCES = ["kernels.cu", "conv_umma.cu", "rbpair_umma.cu", "flow_chain.cu", "enc_chain.cu", "attn_umma.cu", "engine.cu"]
+SOURCES = ["kernels.cu", "conv_umma.cu", "rbpair_umma.cu", "stage_umma.cu", "flow_chain.cu", "enc_chain.cu", "attn_umma.cu", "engine.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

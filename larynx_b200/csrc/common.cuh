@@ -109,4 +109,7 @@ struct ConvBatch {
   ConvParams p[3];
 };
 
+// convs per launch of the per-stage dataflow kernel (stage_umma.cuh): 3 MRF branches x 3 dilations x (c1, c2)
+constexpr int SG_MAX_CONVS = 18;
+
 }  // namespace b2

@@ -234,6 +234,10 @@ struct b200tts_call {
   float *logw_d = nullptr, *xm_d = nullptr;
   // step table of the chained encoder (enc_chain.cuh): pinned host staging + device copy, allocated on first use
   EncStep *enc_steps_h = nullptr, *enc_steps_d = nullptr;
+  // tables + tile flags of the per-stage dataflow kernel (stage_umma.cuh), one set per HiFi-GAN stage, allocated on first use
+  void *stage_tab_h[8] = {}, *stage_tab_d[8] = {};
+  unsigned int* stage_flags[8] = {};
+  size_t stage_flags_cap[8] = {};
   // decode state
   int *idx_d = nullptr, idx_ld = 0;
   float* taps_d = nullptr;
@@ -306,6 +310,8 @@ static void set_out(ConvParams& p, const Planes& pl, float slope, const Planes* 
 //   no_flow_chain flow decoder as one launch per conv instead of the persistent kernel (flow_chain.cuh)
 //   no_enc_chain  text encoder as one launch per layer instead of the persistent kernel (enc_chain.cuh)
 //   no_rbpair     HiFi-GAN ResBlock convs of the narrow stages as two launches instead of the fused kernel (rbpair_umma.cuh)
+//   stage_trace   per-item timeline of one CTA of every stage_umma launch on stderr (single-threaded use)
+//   no_stage      HiFi-GAN ResBlock convs as one launch per conv position instead of one dataflow launch per stage (stage_umma.cuh)
 //   chain_trace   per-layer phase stamps of the persistent kernels on stderr
 //   trace         per-conv %globaltimer phase trace on stderr (single-threaded use; implies no_flow_chain)
 static bool dbg_flag(const char* name) {
@@ -1212,7 +1218,43 @@ static void hifigan_run(const b200tts_hifigan* m, b200tts_call* c, const float* 
       };
       const bool umma_rb = m->resblock == 1 && use_umma() && nk == 3 && m->rb[i * nk].c1[0].wu != nullptr &&
                            !conv_trace();
+      bool staged = false;
       if (umma_rb) {
+        // all ResBlock convs of the stage in one persistent launch with tile-level dataflow (stage_umma.cuh)
+        static const bool no_stage = dbg_flag("no_stage");
+        const int ndil = m->rb[i * nk].ndil;
+        if (!no_stage && 2 * ndil * 3 <= SG_MAX_CONVS && i < 8) {
+          ConvParams tab[SG_MAX_CONVS];
+          bool all_planes = true;
+          for (int d = 0; d < ndil; ++d)
+            for (int j = 0; j < 3; ++j) {
+              bool pl = false;
+              fill_c1(j, d, tab[(2 * d) * 3 + j], pl);
+              bind(tab[(2 * d) * 3 + j], m->rb[i * nk + j].c1[d]);
+              all_planes = all_planes && pl && m->rb[i * nk + j].ndil == ndil;
+              fill_c2(j, d, tab[(2 * d + 1) * 3 + j], pl);
+              bind(tab[(2 * d + 1) * 3 + j], m->rb[i * nk + j].c2[d]);
+            }
+          if (all_planes && stage_umma_supported(tab, 2 * ndil, 3)) {
+            if (!c->stage_tab_h[i]) {
+              B2_CUDA(cudaMallocHost(&c->stage_tab_h[i], stage_umma_table_bytes()));
+              B2_CUDA(cudaMalloc(&c->stage_tab_d[i], stage_umma_table_bytes()));
+            }
+            const size_t need_flags = (size_t)2 * ndil * 3 * batch * ((L + 127) / 128 + 1);
+            if (need_flags > c->stage_flags_cap[i]) {
+              if (c->stage_flags[i]) B2_CUDA(cudaFree(c->stage_flags[i]));
+              c->stage_flags[i] = nullptr;
+              B2_CUDA(cudaMalloc((void**)&c->stage_flags[i], sizeof(unsigned int) * need_flags * 2));
+              c->stage_flags_cap[i] = need_flags * 2;
+            }
+            c->launches += launch_stage_umma(tab, 2 * ndil, 3, batch, frames_h, c->stage_tab_h[i], c->stage_tab_d[i], c->stage_flags[i],
+                                             c->stage_flags_cap[i], s, dbg_flag("stage_trace"));
+            staged = true;
+          }
+        }
+      }
+      if (staged) {
+      } else if (umma_rb) {
         const int ndil = m->rb[i * nk].ndil;
         static const bool no_pair = dbg_flag("no_rbpair");
         for (int d = 0; d < ndil; ++d) {
@@ -1519,6 +1561,7 @@ int b200tts_call_create(int device, b200tts_call** out) {
   conv1d_init_attributes();
   conv_umma_init_attributes();
   rbpair_umma_init_attributes();
+  stage_umma_init_attributes();
   attention_init_attributes();
   attn_umma_init_attributes();
   flow_chain_init_attributes();
@@ -1549,6 +1592,11 @@ int b200tts_call_destroy(b200tts_call* c) {
   }
   cudaFreeHost(c->enc_steps_h);
   cudaFree(c->enc_steps_d);
+  for (int i = 0; i < 8; ++i) {
+    cudaFreeHost(c->stage_tab_h[i]);
+    cudaFree(c->stage_tab_d[i]);
+    cudaFree(c->stage_flags[i]);
+  }
   cudaStreamDestroy(c->stream);
   cudaEventDestroy(c->fork);
   cudaEventDestroy(c->ev0);

@@ -14,6 +14,12 @@ void conv_umma_init_attributes();
 void rbpair_umma_init_attributes();
 bool rbpair_umma_supported(const ConvParams* c1, const ConvParams* c2, int n);
 int launch_rbpair_umma(const ConvParams* c1, const ConvParams* c2, int n, int batch, int Lmax, cudaStream_t stream);
+// all ResBlock convs of a HiFi-GAN stage in one persistent launch with tile-level dataflow (stage_umma.cu)
+void stage_umma_init_attributes();
+bool stage_umma_supported(const ConvParams* convs, int n_levels, int n_cols);
+size_t stage_umma_table_bytes();
+int launch_stage_umma(const ConvParams* convs, int n_levels, int n_cols, int batch, const int* lens_h, void* tab_h, void* tab_d,
+                      unsigned int* flags_d, size_t flags_cap, cudaStream_t s, bool trace = false);
 void attention_init_attributes();
 void attn_umma_init_attributes();
 bool attn_umma_supported(int H, int n_heads, int window, int Tmax);

@@ -1,0 +1,193 @@
+// stage_umma.cu — host side of the per-stage dataflow kernel (stage_umma.cuh): work partition + launch.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "kernels.cuh"
+#include "stage_umma.cuh"
+
+namespace b2 {
+
+void stage_umma_init_attributes() {
+  B2_CUDA(cudaFuncSetAttribute(stage_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  B2_CUDA(cudaFuncSetAttribute(stage_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  B2_CUDA(cudaFuncSetAttribute(stage_umma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+}
+
+static int stage_mt(int nt) { return nt <= 32 ? 4 : (nt <= 64 ? 2 : 1); }
+
+template <int MT>
+static int resident_ctas(size_t smem) {
+  int dev = 0, sms = 0, per_sm = 0;
+  B2_CUDA(cudaGetDevice(&dev));
+  B2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stage_umma_kernel<MT>, SG_EW * 32 + 128, smem));
+  return sms * per_sm;
+}
+
+bool stage_umma_supported(const ConvParams* convs, int n_levels, int n_cols) {
+  const int n = n_levels * n_cols;
+  if (n < 1 || n > SG_MAX_CONVS) return false;
+  const ConvParams& p0 = convs[0];
+  const int C = p0.Cin, NT = p0.um_nt;
+  if (C % 32 != 0 || NT < 32 || NT > 128 || NT % 32 != 0 || p0.Cout % NT != 0) return false;
+  const int mt = stage_mt(NT);
+  for (int i = 0; i < n; ++i) {
+    const ConvParams& p = convs[i];
+    if (p.Cin != C || p.Cout != p0.Cout || p.um_nt != NT || p.um_nsplit != 2 || !p.wu || !p.xp || !p.bias) return false;
+    if (p.epi != EPI_PLAIN || p.pix > 1 || p.n_phase != 1 || p.res || p.x2 || p.x3) return false;
+    if (!(p.yp || p.y) || (p.yp && p.yp_nsplit != 2)) return false;
+    if (((p.K - 1) * p.dil + ((UM_PADL - p.pad_left) & 7) + 7) / 8 * 8 > UM_HALO || p.pad_left > UM_PADL) return false;
+    if ((p.K - 1) * p.dil >= mt * 128) return false;  // a tile only depends on its producer's three neighbouring tiles
+    if (p.lens != p0.lens || p.len_mul != p0.len_mul || !p.lens) return false;
+    if (p.xp_kc < (C + 31) / 32 * 4) return false;
+  }
+  size_t smem = 0;
+  if (mt == 1) smem = StageCfg<1>::smem_bytes(NT, p0.Cout);
+  else if (mt == 2) smem = StageCfg<2>::smem_bytes(NT, p0.Cout);
+  else smem = StageCfg<4>::smem_bytes(NT, p0.Cout);
+  return smem <= 227 * 1024;
+}
+
+size_t stage_umma_table_bytes() {
+  return sizeof(ConvParams) * SG_MAX_CONVS + sizeof(int) * SG_MAX_CONVS + sizeof(int) * 1024 + sizeof(StageSeg) * 2048;
+}
+
+// convs: host table [n_levels][n_cols]; lens_h: host copy of the item lengths (x len_mul = rows); tab_h / tab_d: pinned host and
+// device scratch of stage_umma_table_bytes() (the host block must stay untouched until the stream has consumed the copy);
+// flags_d: at least n_levels * n_cols * batch * ceil(Lmax / (MT*128)) counters.
+int launch_stage_umma(const ConvParams* convs, int n_levels, int n_cols, int batch, const int* lens_h, void* tab_h, void* tab_d,
+                      unsigned int* flags_d, size_t flags_cap, cudaStream_t s, bool trace) {
+  B2_CHECK(stage_umma_supported(convs, n_levels, n_cols), "stage_umma: unsupported stage geometry");
+  const int n = n_levels * n_cols;
+  const ConvParams& p0 = convs[0];
+  const int NT = p0.um_nt, ntiles = p0.Cout / NT, mt = stage_mt(NT);
+  const int nch = (p0.Cin + 31) / 32;
+  // ---- modelled cost of one tile of a column through all levels (units: 10 ns).  Fitted to per-CTA timelines of the full
+  //      launch (profiles/r2d_stage_trace.log: all 148 CTAs busy, L2 shared): the wide stages are main-loop bound (k = 3: epilogue
+  //      bound), the 256-row tiles of the 64-channel stage overlap the two poorly (sum, not max), the
+  //      512-row tiles of the 32-channel stage are epilogue bound for every kernel size.
+  std::vector<long long> wcol(n_cols, 0);
+  for (int j = 0; j < n_cols; ++j)
+    for (int lv = 0; lv < n_levels; ++lv) {
+      const long long kc = (long long)convs[lv * n_cols + j].K * nch;
+      long long cost;
+      if (mt == 1) cost = std::max(26 * kc + 120, 600LL);
+      else if (mt == 2) cost = 55 * kc / 2 + 370;
+      else cost = std::max(50 * kc + 150, 600LL);
+      wcol[j] += cost;
+    }
+  int tiles_max = 0;
+  long long total = 0, n_tiles_all = 0;
+  std::vector<int> mtl(batch);
+  for (int b = 0; b < batch; ++b) {
+    const int Lb = lens_h[b] * p0.len_mul;
+    mtl[b] = (Lb + mt * 128 - 1) / (mt * 128);
+    tiles_max = std::max(tiles_max, mtl[b]);
+    for (int j = 0; j < n_cols; ++j) {
+      total += (long long)mtl[b] * ntiles * wcol[j];
+      n_tiles_all += (long long)mtl[b] * ntiles;
+    }
+  }
+  if (n_tiles_all == 0) return 0;
+  B2_CHECK((size_t)n * batch * tiles_max <= flags_cap, "stage_umma: flag buffer too small");
+  size_t smem = 0;
+  int resident = 0;
+  if (mt == 1) { smem = StageCfg<1>::smem_bytes(NT, p0.Cout); resident = resident_ctas<1>(smem); }
+  else if (mt == 2) { smem = StageCfg<2>::smem_bytes(NT, p0.Cout); resident = resident_ctas<2>(smem); }
+  else { smem = StageCfg<4>::smem_bytes(NT, p0.Cout); resident = resident_ctas<4>(smem); }
+  B2_CHECK(resident >= 1, "stage_umma: kernel does not fit an SM");
+  const int nctas = (int)std::min<long long>(std::min(resident, 1000), n_tiles_all);
+  // ---- contiguous, equal-cost ranges: tile -> CTA by its cumulative cost
+  char* th = reinterpret_cast<char*>(tab_h);
+  ConvParams* convs_t = reinterpret_cast<ConvParams*>(th);
+  int* dep_t = reinterpret_cast<int*>(th + sizeof(ConvParams) * SG_MAX_CONVS);
+  int* off_t = dep_t + SG_MAX_CONVS;
+  StageSeg* seg_t = reinterpret_cast<StageSeg*>(off_t + 1024);
+  B2_CHECK(nctas + 1 <= 1024, "stage_umma: too many CTAs");
+  memcpy(convs_t, convs, sizeof(ConvParams) * n);
+  for (int lv = 0; lv < n_levels; ++lv)
+    for (int j = 0; j < n_cols; ++j) dep_t[lv * n_cols + j] = lv > 0 ? (lv - 1) * n_cols + j : -1;
+  int nseg = 0, cur_cta = -1;
+  long long cum = 0;
+  for (int j = 0; j < n_cols; ++j)
+    for (int b = 0; b < batch; ++b)
+      for (int nt = 0; nt < ntiles; ++nt) {
+        bool open = false;
+        for (int t = 0; t < mtl[b]; ++t) {
+          const int cta = (int)std::min<long long>(nctas - 1, (cum + wcol[j] / 2) * nctas / total);
+          cum += wcol[j];
+          if (cta != cur_cta) {
+            for (int c = cur_cta + 1; c <= cta; ++c) off_t[c] = nseg;  // (CTAs skipped over own no tiles)
+            cur_cta = cta;
+            open = false;
+          }
+          if (!open) {
+            B2_CHECK(nseg < 2048, "stage_umma: too many segments");
+            seg_t[nseg].col = j; seg_t[nseg].b = b; seg_t[nseg].ntile = nt; seg_t[nseg].t_begin = t; seg_t[nseg].t_end = t;
+            ++nseg;
+            open = true;
+          }
+          seg_t[nseg - 1].t_end = t + 1;
+        }
+      }
+  for (int c = cur_cta + 1; c <= nctas; ++c) off_t[c] = nseg;
+  char* td = reinterpret_cast<char*>(tab_d);
+  B2_CUDA(cudaMemcpyAsync(td, th, stage_umma_table_bytes(), cudaMemcpyHostToDevice, s));
+  B2_CUDA(cudaMemsetAsync(flags_d, 0, sizeof(unsigned int) * (size_t)n * batch * tiles_max, s));
+  StageParams sp;
+  sp.convs = reinterpret_cast<const ConvParams*>(td);
+  sp.dep = reinterpret_cast<const int*>(td + sizeof(ConvParams) * SG_MAX_CONVS);
+  sp.seg_off = sp.dep + SG_MAX_CONVS;
+  sp.segs = reinterpret_cast<const StageSeg*>(sp.seg_off + 1024);
+  sp.flags = flags_d;
+  sp.n_levels = n_levels; sp.n_cols = n_cols; sp.zb = batch; sp.tiles_max = tiles_max; sp.ntiles = ntiles;
+  sp.trace = nullptr; sp.trace_cta = 0; sp.trace_items = 0;
+  static unsigned long long* tr = nullptr;
+  constexpr int TR_ITEMS = 64;
+  int trace_cta = 0;
+  if (trace) {  // debug (single-threaded use): per-item stamps of two CTAs, printed after the launch
+    if (!tr) B2_CUDA(cudaMallocManaged(&tr, sizeof(unsigned long long) * 8 * TR_ITEMS));
+    B2_CUDA(cudaDeviceSynchronize());
+    memset(tr, 0, sizeof(unsigned long long) * 8 * TR_ITEMS);
+    const char* e = getenv("B200TTS_TRACE_CTA");  // debug only: which CTA to trace (default: the middle one)
+    trace_cta = e ? std::min(std::max(atoi(e), 0), nctas - 1) : nctas / 2;
+    sp.trace = tr; sp.trace_cta = trace_cta; sp.trace_items = TR_ITEMS;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(nctas);
+  cfg.blockDim = dim3(SG_EW * 32 + 128);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;  // all CTAs resident at once: they wait for each other's tiles
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (mt == 1) B2_CUDA(cudaLaunchKernelEx(&cfg, stage_umma_kernel<1>, sp));
+  else if (mt == 2) B2_CUDA(cudaLaunchKernelEx(&cfg, stage_umma_kernel<2>, sp));
+  else B2_CUDA(cudaLaunchKernelEx(&cfg, stage_umma_kernel<4>, sp));
+  B2_CUDA(cudaGetLastError());
+  if (trace) {
+    B2_CUDA(cudaDeviceSynchronize());
+    unsigned long long t0 = ~0ull, t1 = 0;
+    for (int i = 0; i < 8 * TR_ITEMS; ++i)
+      if (tr[i]) { t0 = std::min(t0, tr[i]); t1 = std::max(t1, tr[i]); }
+    const int c0 = off_t[trace_cta], c1 = off_t[trace_cta + 1];
+    fprintf(stderr, "[stage] NT %d nch %d mt %d: %d CTAs, CTA %d has %d segment(s):", NT, nch, mt, nctas, trace_cta, c1 - c0);
+    for (int q = c0; q < c1; ++q) fprintf(stderr, " (col %d K %d tiles %d-%d)", seg_t[q].col, convs[seg_t[q].col].K, seg_t[q].t_begin, seg_t[q].t_end);
+    fprintf(stderr, "; first stamp to last %.1f us\n", (t1 - t0) * 1e-3);
+    for (int i = 0; i < TR_ITEMS; ++i) {
+      const unsigned long long* e = tr + (size_t)i * 8;
+      if (!e[5]) break;
+      fprintf(stderr, "[stage]  item %2d: dep-wait %6.2f..%6.2f | mma start %6.2f A0 landed %6.2f W0 landed %6.2f issued %6.2f | epi %6.2f..%6.2f\n", i,
+              (e[0] - t0) * 1e-3, (e[1] - t0) * 1e-3, (e[3] - t0) * 1e-3, (e[7] - t0) * 1e-3, (e[2] - t0) * 1e-3, (e[4] - t0) * 1e-3, (e[5] - t0) * 1e-3,
+              (e[6] - t0) * 1e-3);
+    }
+  }
+  return 1;
+}
+
+}  // namespace b2

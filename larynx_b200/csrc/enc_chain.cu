@@ -70,7 +70,10 @@ int launch_enc_chain(const EncStep* steps, const EncChainParams& fp, int max_tx,
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  B2_CUDA(cudaLaunchKernelEx(&cfg, enc_chain_kernel, fp));
+  spin_gate_begin(s);
+  const cudaError_t le = cudaLaunchKernelEx(&cfg, enc_chain_kernel, fp);
+  spin_gate_end(s);
+  B2_CUDA(le);
   B2_CUDA(cudaGetLastError());
   return 1;
 }

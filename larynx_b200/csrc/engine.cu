@@ -906,6 +906,12 @@ static void glow_flow_impl(const b200tts_glow* m, b200tts_call* c, float noise_s
         }
         fprintf(stderr, "\n");
       }
+      for (int c = 0; c < 6; ++c) {  // micro-trace of the MMA warp of CTA (0,0): first res_skip layer and first in_layer, per chunk
+        const unsigned long long *e = tr + ((size_t)(200 + c) * 6) * 8, *f = tr + ((size_t)(210 + c) * 6) * 8;
+        fprintf(stderr, "[chain]   rs chunk %d: wait A %6.2f..%6.2f issued+committed %6.2f | in chunk %d: wait A %6.2f..%6.2f W %6.2f issued+committed %6.2f\n", c,
+                (e[0] - t_start) * 1e-3, (e[1] - t_start) * 1e-3, (e[2] - t_start) * 1e-3, c, (f[0] - t_start) * 1e-3, (f[1] - t_start) * 1e-3,
+                (f[2] - t_start) * 1e-3, (f[3] - t_start) * 1e-3);
+      }
       unsigned long long t_end = 0;
       for (int i = 0; i < 8 * 6 * n_layers; ++i) t_end = std::max(t_end, tr[i]);
       fprintf(stderr, "[chain] %d layers, %.1f us from first barrier to last publish (%.2f us per layer)\n", n_layers,

@@ -57,7 +57,10 @@ int launch_flow_chain(const FlowChainParams& fp, int Lmax, cudaStream_t s) {
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  B2_CUDA(cudaLaunchKernelEx(&cfg, flow_chain_kernel, fp));
+  spin_gate_begin(s);
+  const cudaError_t le = cudaLaunchKernelEx(&cfg, flow_chain_kernel, fp);
+  spin_gate_end(s);
+  B2_CUDA(le);
   B2_CUDA(cudaGetLastError());
   return 1;
 }

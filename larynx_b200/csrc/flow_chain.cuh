@@ -324,11 +324,15 @@ __global__ void __launch_bounds__(FC_THREADS, 1) flow_chain_kernel(const __grid_
           };
           if (K > 1) {  // in_layer: a weight slot = one chunk with all its taps
             for (int c = 0; c < nch; ++c) {
+              const bool mt_ = blk == 0 && step == 1 && lane == 0;  // debug micro-trace of the first in_layer
+              if (mt_) FC_TRACE(210 + c, 0);
               mbar_wait(&a_full[as], aph);
               tc_fence_after();
+              if (mt_) FC_TRACE(210 + c, 1);
               if (c == 0 && lane == 0) FC_TRACE(blk * n_steps + step, 1);
               mbar_wait(&w_full[ws], wph);
               tc_fence_after();
+              if (mt_) FC_TRACE(210 + c, 2);
               if (c == 0 && lane == 0) FC_TRACE(blk * n_steps + step, 2);
               if (elect_one()) {
                 const uint64_t a_c = a_desc0 + ((as * a_stage) >> 4) + roff;
@@ -338,6 +342,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) flow_chain_kernel(const __grid_
                 mma_commit(&a_empty[as]);
               }
               __syncwarp();
+              if (blk == 0 && step == 1 && lane == 0) FC_TRACE(210 + c, 3);
               if (++ws == FC_WST) { ws = 0; wph ^= 1; }
               if (++as == FC_AST) { as = 0; aph ^= 1; }
             }
@@ -348,8 +353,11 @@ __global__ void __launch_bounds__(FC_THREADS, 1) flow_chain_kernel(const __grid_
               if (c0 == 0 && lane == 0) FC_TRACE(blk * n_steps + step, 2);
               const int cnt = min(FC_G1, nch - c0);
               for (int j = 0; j < cnt; ++j) {
+                const bool mt_ = blk == 0 && step == 2 && lane == 0;  // debug micro-trace of the first res_skip layer
+                if (mt_) FC_TRACE(200 + c0 + j, 0);
                 mbar_wait(&a_full[as], aph);
                 tc_fence_after();
+                if (mt_) FC_TRACE(200 + c0 + j, 1);
                 if (c0 + j == 0 && lane == 0) FC_TRACE(blk * n_steps + step, 1);
                 if (elect_one()) {
                   issue(a_desc0 + ((as * a_stage) >> 4) + roff, b_desc0 + ((ws * w_slot + j * w_stage) >> 4), (c0 + j == 0 && st.init) ? 0u : 1u);
@@ -357,6 +365,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) flow_chain_kernel(const __grid_
                   if (j == cnt - 1) mma_commit(&w_empty[ws]);
                 }
                 __syncwarp();
+                if (mt_) FC_TRACE(200 + c0 + j, 2);
                 if (++as == FC_AST) { as = 0; aph ^= 1; }
               }
               if (++ws == FC_WST) { ws = 0; wph ^= 1; }

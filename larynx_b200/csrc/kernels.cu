@@ -2,6 +2,8 @@
 #include <string.h>
 
 #include "conv1d.cuh"
+#include <mutex>
+
 #include "kernels.cuh"
 
 namespace b2 {
@@ -807,6 +809,48 @@ void launch_overlap_add(const float* fr, long long fr_bs, const int* frames, int
   dim3 grid((max_len + 255) / 256, batch);
   overlap_add_kernel<<<grid, 256, 0, s>>>(fr, fr_bs, frames, len_mul, pcm, pcm_ld, peak_bits);
   B2_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-wide ordering of the kernels whose CTAs wait for each other (see kernels.cuh)
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct SpinGate {
+  std::mutex m;
+  cudaEvent_t ev[64] = {};
+  bool has[64] = {};
+};
+SpinGate& spin_gate() {
+  static SpinGate g;
+  return g;
+}
+}  // namespace
+
+void spin_gate_begin(cudaStream_t s) {
+  int dev = 0;
+  B2_CUDA(cudaGetDevice(&dev));
+  B2_CHECK(dev >= 0 && dev < 64, "device index out of range");
+  SpinGate& g = spin_gate();
+  g.m.lock();  // released by spin_gate_end: wait + launch + record are one step with respect to the other host threads
+  if (g.has[dev]) {
+    const cudaError_t e = cudaStreamWaitEvent(s, g.ev[dev], 0);
+    if (e != cudaSuccess) {
+      g.m.unlock();
+      B2_CUDA(e);
+    }
+  }
+}
+
+void spin_gate_end(cudaStream_t s) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  SpinGate& g = spin_gate();
+  cudaError_t e = cudaSuccess;
+  if (!g.ev[dev]) e = cudaEventCreateWithFlags(&g.ev[dev], cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventRecord(g.ev[dev], s);
+  if (e == cudaSuccess) g.has[dev] = true;
+  g.m.unlock();
+  B2_CUDA(e);
 }
 
 }  // namespace b2

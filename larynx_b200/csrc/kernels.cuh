@@ -72,6 +72,14 @@ void launch_mean3_image(const float* x1, const float* x2, const float* x3, long 
                         const int* lens, int len_mul, int batch, void* img, long long img_bs, int kc_total, int rows,
                         cudaStream_t s);
 
+// The persistent kernels whose CTAs wait for each other (enc_chain, flow_chain, stage_umma) need all their CTAs resident.
+// A cooperative launch checks that against an EMPTY device; two such grids from different host threads' streams can each get
+// part of the SMs and then wait for the rest forever (seen with two BatchScheduler workers: bench.py config 5).  The gate
+// orders them device-wide without blocking the host: a launch between begin/end waits (cudaStreamWaitEvent) for the previous
+// gated launch of any stream on this device.  Kernels that never wait for other CTAs may still overlap them.
+void spin_gate_begin(cudaStream_t s);
+void spin_gate_end(cudaStream_t s);
+
 // the whole flow decoder in one persistent cooperative launch (flow_chain.cu)
 struct FlowChainParams;
 void flow_chain_init_attributes();

@@ -166,9 +166,13 @@ int launch_stage_umma(const ConvParams* convs, int n_levels, int n_cols, int bat
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (mt == 1) B2_CUDA(cudaLaunchKernelEx(&cfg, stage_umma_kernel<1>, sp));
-  else if (mt == 2) B2_CUDA(cudaLaunchKernelEx(&cfg, stage_umma_kernel<2>, sp));
-  else B2_CUDA(cudaLaunchKernelEx(&cfg, stage_umma_kernel<4>, sp));
+  spin_gate_begin(s);
+  cudaError_t le;
+  if (mt == 1) le = cudaLaunchKernelEx(&cfg, stage_umma_kernel<1>, sp);
+  else if (mt == 2) le = cudaLaunchKernelEx(&cfg, stage_umma_kernel<2>, sp);
+  else le = cudaLaunchKernelEx(&cfg, stage_umma_kernel<4>, sp);
+  spin_gate_end(s);
+  B2_CUDA(le);
   B2_CUDA(cudaGetLastError());
   if (trace) {
     B2_CUDA(cudaDeviceSynchronize());

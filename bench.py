@@ -559,9 +559,11 @@ def bench_ours(args, rank, world, local_rank):
                          "frac": voc_tflops / tensor_peak,
                          "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
                          "traffic_note": (traffic.get("note") if traffic else "no ncu --set full capture of the current kernels committed yet"),
+                         "traffic_unit": "bytes per stage_umma_kernel launch (dram__bytes_read.sum + dram__bytes_write.sum, mean of the 4 stage launches)",
                          "peak_source": peak_src + " bf16 dense (burst)",
-                         "kernel": f"conv_umma_kernel<MT,NSPLIT,EW,WST,AST,G,NBUF> (tcgen05 kind::f16, bf16 hi/lo split = 3 products per algorithmic MAC "
-                                   f"issued as 2 wide-N MMAs, fp32 TMEM accumulators, persistent double-buffered launches for the long stages): HiFi-GAN pass ({voc_launches} launches, {vms:.3f} ms, {HIFIGAN_MFLOP_PER_FRAME:.1f} MFLOP/frame x {frames} frames)",
+                         "kernel": f"stage_umma_kernel<MT> x 4 (one persistent dataflow launch per HiFi-GAN stage: tcgen05 kind::f16, bf16 hi/lo split = 3 products per "
+                                   f"algorithmic MAC issued as 2 wide-N MMAs, fp32 TMEM accumulators double buffered) + conv_umma_kernel (conv_pre, upsamplers): HiFi-GAN pass "
+                                   f"({voc_launches} launches, {vms:.3f} ms, {HIFIGAN_MFLOP_PER_FRAME:.1f} MFLOP/frame x {frames} frames)",
                          "tensor_flops_issued_tflops": 3 * voc_tflops, "frac_tensor_issued": 3 * voc_tflops / tensor_peak,
                          "fp32_simt_peak_tflops": FP32_SIMT_PEAK_TFLOPS, "frac_of_fp32_simt_peak": voc_tflops / FP32_SIMT_PEAK_TFLOPS,
                          "step_tflops": step_flops / (ms_per_utt * 1e-3) / 1e12,

@@ -460,6 +460,31 @@ def test_reentrant_from_host_threads():
         assert np.array_equal(e, g_)
 
 
+@pytest.mark.timeout(300)
+def test_concurrent_batches_from_two_threads_finish():
+    """Two host threads, each with its own call (stream), run micro-batches of long sentences at the same time: the persistent
+    kernels of both (encoder chain, flow chain, one dataflow launch per HiFi-GAN stage) need every CTA resident; without the
+    device-wide gate (kernels.cu: spin_gate) two such grids could interleave and wait for each other forever (bench.py
+    config 5 hung).  Results must equal the single-threaded ones."""
+    glow, voc = common.product_glow(), common.product_hifi()
+    glue = host.MelGlue.from_config(common.glow_cfg()["audio"])
+    rows = [[synth.bench_ids(int(n), seed=900 + 17 * t + i) for i, n in enumerate((96, 120, 77, 128, 64, 101, 88, 115))] for t in range(2)]
+    expect = [host.synthesize_batch(glow, voc, glue, r, seed=11)["audio"] for r in rows]
+    got = [None, None]
+
+    def work(t):
+        for _ in range(12):
+            got[t] = host.synthesize_batch(glow, voc, glue, rows[t], seed=11)["audio"]
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(2)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for e, g_ in zip(expect, got):
+        assert len(e) == len(g_)
+        for a, b_ in zip(e, g_):
+            assert np.array_equal(a, b_)
+
+
 def test_simt_reference_path_still_matches():
     """The fp32 SIMT conv path (B200TTS_DEBUG=simt) is kept as an in-library cross-check of the tensor-core path."""
     import subprocess
@@ -486,6 +511,50 @@ def test_simt_reference_path_still_matches():
     assert outs["simt"]["mel"].shape == outs["umma"]["mel"].shape
     assert np.abs(outs["simt"]["mel"] - outs["umma"]["mel"]).max() <= TOL_MEL
     assert np.abs(outs["simt"]["pcm"] - outs["umma"]["pcm"]).max() <= TOL_E2E  # each path glues its own mel
+
+
+def test_vocoder_launch_schemes_agree_bit_for_bit():
+    """The HiFi-GAN ResBlocks run as one dataflow launch per stage (stage_umma.cuh, the default), as fused c1->c2 steps for the
+    narrow stages (rbpair_umma.cuh, B200TTS_DEBUG=no_stage) or as one launch per conv position (no_stage,no_rbpair).  All three
+    execute the same MMAs in the same order with the same epilogue arithmetic: the waveforms must be identical, for a single
+    utterance and for a ragged batch (different tile ranges per item, tiles that end inside a 128-row block)."""
+    import subprocess
+    import sys
+    import tempfile
+
+    code = """
+import sys
+import numpy as np
+sys.path.insert(0, '.')
+from tests import common
+from larynx_b200 import engine
+v = common.product_hifi()
+call = engine.CALLS.get(0)
+rs = np.random.RandomState(5)
+lens = [131, 47, 300]
+T = max(lens)
+batch = np.zeros((3, 80, T), np.float32)
+for i, n in enumerate(lens):
+    batch[i, :, :n] = rs.randn(80, n) * 2 - 5
+one = v.mels_to_float(batch[0:1, :, :lens[0]])
+hop = v.model.hop
+many = np.zeros((3, T * hop), np.float32)
+v.model.infer(call, batch, np.array(lens, np.int32), 3, T, many, None, T * hop)
+np.savez(sys.argv[1], one=one, many=many)
+"""
+    outs = {}
+    for mode in ("", "no_stage", "no_stage,no_rbpair"):
+        f = os.path.join(tempfile.mkdtemp(), "o.npz")
+        subprocess.run([sys.executable, "-c", code, f], check=True, env=dict(os.environ, B200TTS_DEBUG=mode),
+                       cwd=os.path.dirname(os.path.dirname(__file__)))
+        outs[mode] = np.load(f)
+    for mode in ("no_stage", "no_stage,no_rbpair"):
+        assert np.array_equal(outs[""]["one"], outs[mode]["one"]), mode
+        assert np.array_equal(outs[""]["many"], outs[mode]["many"]), mode
+    many = outs[""]["many"]
+    assert np.isfinite(many).all() and np.abs(outs[""]["one"]).max() > 1e-3
+    assert np.array_equal(many[0, : 131 * 256], outs[""]["one"])  # an item of a ragged batch == the same item alone
+    assert not many[1, 47 * 256:].any()  # nothing behind an item's length
 
 
 def test_device_resident_buffers():

@@ -742,7 +742,7 @@ static void glow_encode_impl(const b200tts_glow* m, b200tts_call* c, const int64
     conv(c, p, e.qkv, batch, max_tx, s);
     if (um_att && e.relk_img) {
       launch_attn_umma(QKV_p.ptr, QKV_p.bs, QKV_p.kc, QKV_p.rows, e.relk_img, e.relv_img, m->window, H, m->n_heads, lens, batch,
-                       ATT_p.ptr, ATT_p.bs, ATT_p.kc, ATT_p.rows, nullptr, 0, 0, s);
+                       ATT_p.ptr, ATT_p.bs, ATT_p.kc, ATT_p.rows, nullptr, 0, 0, s, max_tx);
     } else {
       launch_rel_attention(QKV, (long long)3 * H * ld, ld, H, m->n_heads, e.rel_k, e.rel_v, m->window, lens, batch,
                            max_tx, ATT, (long long)H * ld, ld, s);

@@ -26,7 +26,7 @@ bool attn_umma_supported(int H, int n_heads, int window, int Tmax);
 void launch_attn_umma(const void* qkv_p, long long qkv_bs, int qkv_kc, int qkv_rows, const void* relk_img,
                       const void* relv_img, int window, int H, int n_heads, const int* lens,
                       int batch, void* out_p, long long out_bs, int out_kc, int out_rows, float* out, long long out_fbs,
-                      int out_ld, cudaStream_t s);
+                      int out_ld, cudaStream_t s, int Tmax);
 
 void launch_embed(const long long* ids, const int* lens, int batch, int max_tx, const float* emb, int n_vocab, int H,
                   float* x, long long x_bs, int x_ld, int* bad_id, cudaStream_t s);

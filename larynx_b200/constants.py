@@ -58,3 +58,33 @@ except Exception:  # noqa: BLE001 - larynx (or one of its imports) is not availa
 
         def mels_to_audio(self, mels, settings=None):
             raise NotImplementedError
+
+
+# Generator architectures of the released vocoders (the `-q high | medium | low` choices of the reference CLI,
+# hifi_gan/<name>/config.json): needed to build a vocoder from a bare generator.pth whose directory has no config.json.
+HIFIGAN_CONFIGS = {
+    "universal_large": {
+        "resblock": "1",
+        "upsample_rates": [8, 8, 2, 2],
+        "upsample_kernel_sizes": [16, 16, 4, 4],
+        "upsample_initial_channel": 512,
+        "resblock_kernel_sizes": [3, 7, 11],
+        "resblock_dilation_sizes": [[1, 3, 5], [1, 3, 5], [1, 3, 5]],
+    },
+    "vctk_medium": {
+        "resblock": "1",
+        "upsample_rates": [8, 8, 2, 2],
+        "upsample_kernel_sizes": [16, 16, 4, 4],
+        "upsample_initial_channel": 128,
+        "resblock_kernel_sizes": [3, 7, 11],
+        "resblock_dilation_sizes": [[1, 3, 5], [1, 3, 5], [1, 3, 5]],
+    },
+    "vctk_small": {
+        "resblock": "2",
+        "upsample_rates": [8, 8, 4],
+        "upsample_kernel_sizes": [16, 16, 8],
+        "upsample_initial_channel": 256,
+        "resblock_kernel_sizes": [3, 5, 7],
+        "resblock_dilation_sizes": [[1, 2], [2, 6], [3, 12]],
+    },
+}

@@ -122,7 +122,7 @@ def _effective_config(cfg: dict) -> dict:
     """The reference loads the vocoder config with dataclasses-json, which silently drops unknown keys:
     the flat jik876 json of universal_large (local/hifi_gan/universal_large/config.json) therefore yields
     the *defaults* of hifi_gan/config.py:29-40.  Nested configs ({"model": {...}}) are used as given."""
-    from .synth import HIFIGAN_CONFIGS
+    from .constants import HIFIGAN_CONFIGS
 
     model = dict(HIFIGAN_CONFIGS["universal_large"])
     model.update(cfg.get("model", {}) if isinstance(cfg.get("model"), dict) else {})

@@ -27,6 +27,8 @@ from typing import Dict, Optional
 
 import numpy as np
 
+from .constants import HIFIGAN_CONFIGS  # noqa: F401  (re-exported for tests / bench)
+
 # Architecture constants shared by all 51 shipped voices
 # (local/en-us/ljspeech-glow_tts/config.json:36-62).
 GLOW_DEFAULT_MODEL = {
@@ -79,34 +81,6 @@ GLOW_DEFAULT_AUDIO = {
 }
 
 # hifi_gan/config.py:29-40 defaults == local/hifi_gan/universal_large/config.json:2,10-14
-HIFIGAN_CONFIGS = {
-    "universal_large": {
-        "resblock": "1",
-        "upsample_rates": [8, 8, 2, 2],
-        "upsample_kernel_sizes": [16, 16, 4, 4],
-        "upsample_initial_channel": 512,
-        "resblock_kernel_sizes": [3, 7, 11],
-        "resblock_dilation_sizes": [[1, 3, 5], [1, 3, 5], [1, 3, 5]],
-    },
-    "vctk_medium": {
-        "resblock": "1",
-        "upsample_rates": [8, 8, 2, 2],
-        "upsample_kernel_sizes": [16, 16, 4, 4],
-        "upsample_initial_channel": 128,
-        "resblock_kernel_sizes": [3, 7, 11],
-        "resblock_dilation_sizes": [[1, 3, 5], [1, 3, 5], [1, 3, 5]],
-    },
-    "vctk_small": {
-        "resblock": "2",
-        "upsample_rates": [8, 8, 4],
-        "upsample_kernel_sizes": [16, 16, 8],
-        "upsample_initial_channel": 256,
-        "resblock_kernel_sizes": [3, 5, 7],
-        "resblock_dilation_sizes": [[1, 2], [2, 6], [3, 12]],
-    },
-}
-
-
 def glow_config(num_symbols: int = 46, **model_overrides) -> dict:
     """A full reference-format GlowTTS config.json dict."""
     model = dict(GLOW_DEFAULT_MODEL)

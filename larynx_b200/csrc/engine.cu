@@ -311,6 +311,7 @@ static void set_out(ConvParams& p, const Planes& pl, float slope, const Planes* 
 //   no_enc_chain  text encoder as one launch per layer instead of the persistent kernel (enc_chain.cuh)
 //   no_rbpair     HiFi-GAN ResBlock convs of the narrow stages as two launches instead of the fused kernel (rbpair_umma.cuh)
 //   stage_trace   per-item timeline of one CTA of every stage_umma launch on stderr (single-threaded use)
+//   no_stage_pair the 32-channel HiFi-GAN stage as one item per conv instead of one per ResBlock step (stage_pair_kernel)
 //   no_stage      HiFi-GAN ResBlock convs as one launch per conv position instead of one dataflow launch per stage (stage_umma.cuh)
 //   chain_trace   per-layer phase stamps of the persistent kernels on stderr
 //   trace         per-conv %globaltimer phase trace on stderr (single-threaded use; implies no_flow_chain)
@@ -1241,7 +1242,30 @@ static void hifigan_run(const b200tts_hifigan* m, b200tts_call* c, const float* 
               fill_c2(j, d, tab[(2 * d + 1) * 3 + j], pl);
               bind(tab[(2 * d + 1) * 3 + j], m->rb[i * nk + j].c2[d]);
             }
-          if (all_planes && stage_umma_supported(tab, 2 * ndil, 3)) {
+          // 32-channel stage: whole ResBlock steps per item (T in shared memory); x ping-pongs U -> R -> T(free) -> fp32 R
+          ConvParams f1[9], f2[9];
+          static const bool no_pair_stage = dbg_flag("no_stage_pair");
+          bool pair = !no_pair_stage && all_planes && ndil <= 3 && cout <= 32;
+          if (pair) {
+            for (int d = 0; d < ndil; ++d)
+              for (int j = 0; j < 3; ++j) {
+                const Planes& in = d == 0 ? U_p : ((d & 1) ? R_p[j] : T_p[j]);
+                const Planes& out = (d & 1) ? T_p[j] : R_p[j];
+                ConvParams& a = f1[d * 3 + j];
+                ConvParams& q = f2[d * 3 + j];
+                a = tab[(2 * d) * 3 + j];
+                q = tab[(2 * d + 1) * 3 + j];
+                set_in(a, in);
+                a.yp = nullptr;
+                a.yp_slope = 0.1f;  // T = leaky_relu(c1(.), 0.1), kept on the SM
+                q.xp = nullptr;
+                q.rp = in.ptr; q.rp_bs = in.bs; q.rp_kc = in.kc; q.rp_rows = in.rows; q.rp_inv_slope = 10.f;
+                q.yp = nullptr;
+                if (d + 1 < ndil) set_out(q, out, 0.1f);
+              }
+            pair = stage_pair_supported(f1, f2, ndil, 3);
+          }
+          if (pair || (all_planes && stage_umma_supported(tab, 2 * ndil, 3))) {
             if (!c->stage_tab_h[i]) {
               B2_CUDA(cudaMallocHost(&c->stage_tab_h[i], stage_umma_table_bytes()));
               B2_CUDA(cudaMalloc(&c->stage_tab_d[i], stage_umma_table_bytes()));
@@ -1253,8 +1277,12 @@ static void hifigan_run(const b200tts_hifigan* m, b200tts_call* c, const float* 
               B2_CUDA(cudaMalloc((void**)&c->stage_flags[i], sizeof(unsigned int) * need_flags * 2));
               c->stage_flags_cap[i] = need_flags * 2;
             }
-            c->launches += launch_stage_umma(tab, 2 * ndil, 3, batch, frames_h, c->stage_tab_h[i], c->stage_tab_d[i], c->stage_flags[i],
-                                             c->stage_flags_cap[i], s, dbg_flag("stage_trace"));
+            if (pair)
+              c->launches += launch_stage_pair(f1, f2, ndil, 3, batch, frames_h, c->stage_tab_h[i], c->stage_tab_d[i], c->stage_flags[i],
+                                               c->stage_flags_cap[i], s);
+            else
+              c->launches += launch_stage_umma(tab, 2 * ndil, 3, batch, frames_h, c->stage_tab_h[i], c->stage_tab_d[i], c->stage_flags[i],
+                                               c->stage_flags_cap[i], s, dbg_flag("stage_trace"));
             staged = true;
           }
         }

@@ -20,6 +20,10 @@ bool stage_umma_supported(const ConvParams* convs, int n_levels, int n_cols);
 size_t stage_umma_table_bytes();
 int launch_stage_umma(const ConvParams* convs, int n_levels, int n_cols, int batch, const int* lens_h, void* tab_h, void* tab_d,
                       unsigned int* flags_d, size_t flags_cap, cudaStream_t s, bool trace = false);
+// ... and with a whole ResBlock step (c1 -> c2, T in shared memory) per item for the 32-channel stage
+bool stage_pair_supported(const ConvParams* c1, const ConvParams* c2, int n_levels, int n_cols);
+int launch_stage_pair(const ConvParams* c1, const ConvParams* c2, int n_levels, int n_cols, int batch, const int* lens_h, void* tab_h,
+                      void* tab_d, unsigned int* flags_d, size_t flags_cap, cudaStream_t s);
 void attention_init_attributes();
 void attn_umma_init_attributes();
 bool attn_umma_supported(int H, int n_heads, int window, int Tmax);

@@ -14,6 +14,7 @@ void stage_umma_init_attributes() {
   B2_CUDA(cudaFuncSetAttribute(stage_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   B2_CUDA(cudaFuncSetAttribute(stage_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   B2_CUDA(cudaFuncSetAttribute(stage_umma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  B2_CUDA(cudaFuncSetAttribute(stage_pair_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 }
 
 static int stage_mt(int nt) { return nt <= 32 ? 4 : (nt <= 64 ? 2 : 1); }
@@ -139,6 +140,7 @@ int launch_stage_umma(const ConvParams* convs, int n_levels, int n_cols, int bat
   B2_CUDA(cudaMemsetAsync(flags_d, 0, sizeof(unsigned int) * (size_t)n * batch * tiles_max, s));
   StageParams sp;
   sp.convs = reinterpret_cast<const ConvParams*>(td);
+  sp.convs1 = nullptr;
   sp.dep = reinterpret_cast<const int*>(td + sizeof(ConvParams) * SG_MAX_CONVS);
   sp.seg_off = sp.dep + SG_MAX_CONVS;
   sp.segs = reinterpret_cast<const StageSeg*>(sp.seg_off + 1024);
@@ -191,6 +193,127 @@ int launch_stage_umma(const ConvParams* convs, int n_levels, int n_cols, int bat
               (e[6] - t0) * 1e-3);
     }
   }
+  return 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pair mode (stage_pair_kernel): items are whole ResBlock steps; c1[lv][col], c2[lv][col] with lv = dilation step
+// ------------------------------------------------------------------------------------------------
+static size_t pair_smem(int NT, int C, int n) { return RbPairCfg<4>::smem_bytes(NT, C) + 8 * (size_t)n * C; }
+
+bool stage_pair_supported(const ConvParams* c1, const ConvParams* c2, int n_levels, int n_cols) {
+  const int n = n_levels * n_cols;
+  if (n < 1 || 2 * n > SG_MAX_CONVS) return false;
+  const int C = c1[0].Cin;
+  if (C != 32) return false;  // the 512-row tile variant; the 64-channel stage gains nothing (its main loops dominate)
+  for (int i = 0; i < n; ++i) {
+    const ConvParams &a = c1[i], &b = c2[i];
+    if (a.Cin != C || a.Cout != C || b.Cin != C || b.Cout != C || a.um_nt != C || b.um_nt != C) return false;
+    if (a.um_nsplit != 2 || b.um_nsplit != 2 || !a.wu || !b.wu || !a.xp || !b.rp || !a.bias || !b.bias) return false;
+    if (b.dil != 1 || b.K - 1 > RP_TPAD || (a.K - 1) * a.dil > UM_HALO - 16 || a.pad_left + b.pad_left > UM_PADL) return false;
+    if (a.epi != EPI_PLAIN || b.epi != EPI_PLAIN || a.pix > 1 || b.pix > 1 || b.act != ACT_NONE || b.res) return false;
+    if (!a.lens || a.lens != c1[0].lens || b.lens != a.lens || a.len_mul != c1[0].len_mul || b.len_mul != a.len_mul) return false;
+    if (!(b.yp || b.y) || (b.yp && (b.yp == a.xp || b.yp_nsplit != 2))) return false;
+    if (b.K != c2[i % n_cols].K || a.K != b.K) return false;  // one tile stride per branch
+  }
+  return pair_smem(C, C, n) <= 227 * 1024;
+}
+
+int launch_stage_pair(const ConvParams* c1, const ConvParams* c2, int n_levels, int n_cols, int batch, const int* lens_h, void* tab_h,
+                      void* tab_d, unsigned int* flags_d, size_t flags_cap, cudaStream_t s) {
+  B2_CHECK(stage_pair_supported(c1, c2, n_levels, n_cols), "stage_pair: unsupported stage geometry");
+  constexpr int mt = 4;
+  const int n = n_levels * n_cols;
+  const int C = c1[0].Cin, nch = (C + 31) / 32;
+  // cost of one tile of a branch through all steps (10 ns): main loops of c1 and c2 + the T hand-over in between, or the
+  // output epilogue, whichever is longer (profiles/r2d_stage_trace.log: 0.5 us per tap and chunk, ~5 us per stored tile)
+  std::vector<long long> wcol(n_cols, 0);
+  std::vector<int> S(n_cols);
+  for (int j = 0; j < n_cols; ++j) {
+    S[j] = mt * 128 - (c2[j].K - 1);
+    for (int lv = 0; lv < n_levels; ++lv) wcol[j] += std::max(100LL * c2[lv * n_cols + j].K * nch + 500, 550LL);
+  }
+  int tiles_max = 0;
+  long long total = 0, n_tiles_all = 0;
+  std::vector<int> mtl((size_t)batch * n_cols);
+  for (int b = 0; b < batch; ++b)
+    for (int j = 0; j < n_cols; ++j) {
+      const int Lb = lens_h[b] * c2[0].len_mul;
+      const int t = (Lb + S[j] - 1) / S[j];
+      mtl[(size_t)b * n_cols + j] = t;
+      tiles_max = std::max(tiles_max, t);
+      total += (long long)t * wcol[j];
+      n_tiles_all += t;
+      B2_CHECK(c1[j].xp_rows >= UM_PADL + t * S[j] + mt * 128 + UM_HALO, "stage_pair: input plane image too short");
+    }
+  if (n_tiles_all == 0) return 0;
+  B2_CHECK((size_t)n * batch * tiles_max <= flags_cap, "stage_pair: flag buffer too small");
+  const size_t smem = pair_smem(C, C, n);
+  int dev = 0, sms = 0, per_sm = 0;
+  B2_CUDA(cudaGetDevice(&dev));
+  B2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stage_pair_kernel<4>, SG_EW * 32 + 128, smem));
+  B2_CHECK(per_sm >= 1, "stage_pair: kernel does not fit an SM");
+  const int nctas = (int)std::min<long long>(std::min(sms * per_sm, 1000), n_tiles_all);
+  char* th = reinterpret_cast<char*>(tab_h);
+  ConvParams* convs_t = reinterpret_cast<ConvParams*>(th);  // [0, n): c2 of each step, [n, 2n): c1
+  int* dep_t = reinterpret_cast<int*>(th + sizeof(ConvParams) * SG_MAX_CONVS);
+  int* off_t = dep_t + SG_MAX_CONVS;
+  StageSeg* seg_t = reinterpret_cast<StageSeg*>(off_t + 1024);
+  memcpy(convs_t, c2, sizeof(ConvParams) * n);
+  memcpy(convs_t + n, c1, sizeof(ConvParams) * n);
+  for (int lv = 0; lv < n_levels; ++lv)
+    for (int j = 0; j < n_cols; ++j) dep_t[lv * n_cols + j] = lv > 0 ? (lv - 1) * n_cols + j : -1;
+  int nseg = 0, cur_cta = -1;
+  long long cum = 0;
+  for (int j = 0; j < n_cols; ++j)
+    for (int b = 0; b < batch; ++b) {
+      bool open = false;
+      for (int t = 0; t < mtl[(size_t)b * n_cols + j]; ++t) {
+        const int cta = (int)std::min<long long>(nctas - 1, (cum + wcol[j] / 2) * nctas / total);
+        cum += wcol[j];
+        if (cta != cur_cta) {
+          for (int c = cur_cta + 1; c <= cta; ++c) off_t[c] = nseg;
+          cur_cta = cta;
+          open = false;
+        }
+        if (!open) {
+          B2_CHECK(nseg < 2048, "stage_pair: too many segments");
+          seg_t[nseg].col = j; seg_t[nseg].b = b; seg_t[nseg].ntile = 0; seg_t[nseg].t_begin = t; seg_t[nseg].t_end = t;
+          ++nseg;
+          open = true;
+        }
+        seg_t[nseg - 1].t_end = t + 1;
+      }
+    }
+  for (int c = cur_cta + 1; c <= nctas; ++c) off_t[c] = nseg;
+  char* td = reinterpret_cast<char*>(tab_d);
+  B2_CUDA(cudaMemcpyAsync(td, th, stage_umma_table_bytes(), cudaMemcpyHostToDevice, s));
+  B2_CUDA(cudaMemsetAsync(flags_d, 0, sizeof(unsigned int) * (size_t)n * batch * tiles_max, s));
+  StageParams sp;
+  sp.convs = reinterpret_cast<const ConvParams*>(td);
+  sp.convs1 = sp.convs + n;
+  sp.dep = reinterpret_cast<const int*>(td + sizeof(ConvParams) * SG_MAX_CONVS);
+  sp.seg_off = sp.dep + SG_MAX_CONVS;
+  sp.segs = reinterpret_cast<const StageSeg*>(sp.seg_off + 1024);
+  sp.flags = flags_d;
+  sp.n_levels = n_levels; sp.n_cols = n_cols; sp.zb = batch; sp.tiles_max = tiles_max; sp.ntiles = 1;
+  sp.trace = nullptr; sp.trace_cta = 0; sp.trace_items = 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(nctas);
+  cfg.blockDim = dim3(SG_EW * 32 + 128);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;  // all CTAs resident at once: they wait for each other's tiles
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  spin_gate_begin(s);
+  const cudaError_t le = cudaLaunchKernelEx(&cfg, stage_pair_kernel<4>, sp);
+  spin_gate_end(s);
+  B2_CUDA(le);
+  B2_CUDA(cudaGetLastError());
   return 1;
 }
 

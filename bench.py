@@ -6,7 +6,7 @@
 Headline workload = BASELINE.json configs[1]: en-us/ljspeech GlowTTS + hifi_gan/universal_large architecture (synthetic
 weights, there is no network for checkpoints), ONE 128-phoneme sentence at batch 1, fp32: phoneme ids -> mel (~502
 frames, 5.8 s of audio) -> 22.05 kHz PCM.  One "step" = UTT_PER_STEP of those utterances one after the other, each at
-batch 1 (a single utterance takes ~3 ms: twenty of them would be a 60 ms timed region), L2 flushed (untimed) before
+batch 1 (a single utterance takes ~3 ms: twenty of them would be a 60 ms timed region; 20 x 24 make ~1.4 s), L2 flushed (untimed) before
 every utterance.
 
 Metric: mel-frames/s (whole job, all GPUs); the same line carries RTF and x-real-time.
@@ -37,7 +37,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_IDS = 128
-UTT_PER_STEP = 16
+UTT_PER_STEP = 24   # 20 steps x 24 utterances x ~3 ms: a timed region of ~1.4 s
 NOISE_SCALE, LENGTH_SCALE = 0.667, 1.0
 HIFIGAN_MFLOP_PER_FRAME = 614.105088  # HiFi-GAN universal_large, exact 2*MAC count
 FLOW_MFLOP_PER_FRAME = 21.351936      # flow decoder

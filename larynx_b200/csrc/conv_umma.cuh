@@ -13,7 +13,8 @@
 //     fewer, wider MMAs are what narrow layers need);
 //   * activations, "plane" mode: the PRODUCING layer's epilogue already wrote the bf16 hi/lo planes of its
 //     (pre-activated) output in image order [plane][C/8][PADL + rows][8] to global memory, so the consumer's A
-//     tile is 2*4 contiguous bulk copies per 32-channel chunk — no SM instructions on the operand path;
+//     tile is 2*4 contiguous bulk copies per 32-channel chunk (from the 128-byte boundary below its first row) — no SM
+//     instructions on the operand path;
 //   * activations, "gather" mode (inputs produced by non-conv kernels): the epilogue warps read fp32 [C][L], apply the
 //     pre-op, split and write the image to smem themselves.
 //
@@ -24,7 +25,8 @@
 //                   of the next conv (including the zero rows that implement the reference's padding/masking);
 //   warp EW       : MMA issuer (one elected lane): tcgen05.mma.cta_group::1.kind::f16, one accumulator per magnitude class;
 //   warp EW+1     : lane 0: weight bulk copies;
-//   warp EW+2     : (NBUF = 2 only) lane 0: activation bulk copies; with NBUF = 1 thread 0 issues them for its one tile.
+//   warp EW+2     : (NBUF = 2 only) activation bulk copies, one copy per lane (issue_a_chunks); with NBUF = 1 warp 0 issues them
+//                   for its one tile before it joins the epilogue.
 // Pipelines: A ring (AST stages, per ci-chunk of 32 channels, reused by all K taps), W ring (WST slots of G taps),
 // accumulator full/empty barriers per TMEM buffer (NBUF = 2: the MMA warp fills one buffer while the epilogue warps drain
 // the other and the rings run ahead into the CTA's next time tile).  All waits are mbarrier based; tcgen05.commit

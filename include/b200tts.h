@@ -103,6 +103,12 @@ int b200tts_glow_flow_tap(const b200tts_glow* m, b200tts_call* call, int blk, fl
  * adds to frame f of channel c of item b.  Exists so that the generator's moments can be tested. */
 int b200tts_debug_noise(b200tts_call* call, uint64_t seed, int batch, int mel, int n, float* out, int ld);
 
+/* Host logic of the per-stage HiFi-GAN kernels on its own (no device needed, no reference counterpart): how the time tiles of
+ * `n_strips` strips (strip i: strip_tiles[i] tiles of modelled cost strip_cost[i] each) are cut into contiguous, equal-cost
+ * ranges for `nctas` CTAs.  cta_of_tile [sum of strip_tiles], in strip order; returns 0 and writes the number of ranges. */
+int b200tts_debug_stage_partition(const int32_t* strip_tiles, const int64_t* strip_cost, int n_strips, int nctas,
+                                  int32_t* cta_of_tile, int32_t* n_ranges);
+
 /* ---- HiFi-GAN (hifi_gan/models.py:186-202 Generator.forward) ------------------------------ */
 int b200tts_hifigan_create(const void* blob, size_t nbytes, int device, b200tts_hifigan** out);
 int b200tts_hifigan_destroy(b200tts_hifigan* m);

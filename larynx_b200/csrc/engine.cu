@@ -1744,6 +1744,16 @@ int b200tts_debug_noise(b200tts_call* c, uint64_t seed, int batch, int mel, int 
   B2_API_END
 }
 
+int b200tts_debug_stage_partition(const int32_t* strip_tiles, const int64_t* strip_cost, int n_strips, int nctas,
+                                  int32_t* cta_of_tile, int32_t* n_ranges) {
+  B2_API_BEGIN
+  static_assert(sizeof(long long) == sizeof(int64_t) && sizeof(int) == sizeof(int32_t), "ABI types");
+  const int n = stage_partition_debug(reinterpret_cast<const int*>(strip_tiles), reinterpret_cast<const long long*>(strip_cost), n_strips, nctas,
+                                      reinterpret_cast<int*>(cta_of_tile));
+  if (n_ranges) *n_ranges = n;
+  B2_API_END
+}
+
 int b200tts_glow_flow_tap(const b200tts_glow* m, b200tts_call* c, int blk, float* out, int ld) {
   B2_API_BEGIN
   B2_CHECK(m && c && out, "null argument");

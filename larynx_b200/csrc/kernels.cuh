@@ -24,6 +24,11 @@ int launch_stage_umma(const ConvParams* convs, int n_levels, int n_cols, int bat
 bool stage_pair_supported(const ConvParams* c1, const ConvParams* c2, int n_levels, int n_cols);
 int launch_stage_pair(const ConvParams* c1, const ConvParams* c2, int n_levels, int n_cols, int batch, const int* lens_h, void* tab_h,
                       void* tab_d, unsigned int* flags_d, size_t flags_cap, cudaStream_t s);
+// host logic of the stage kernels' work split, exposed for tests (b200tts_debug_stage_partition)
+struct StageStrip;
+struct StageSeg;
+int stage_partition(const StageStrip* strips, int n_strips, int nctas, int* seg_off, StageSeg* segs, int max_segs);
+int stage_partition_debug(const int* strip_tiles, const long long* strip_cost, int n_strips, int nctas, int* cta_of_tile);
 void attention_init_attributes();
 void attn_umma_init_attributes();
 bool attn_umma_supported(int H, int n_heads, int window, int Tmax);

@@ -28,6 +28,44 @@ static int resident_ctas(size_t smem) {
   return sms * per_sm;
 }
 
+// Contiguous, equal-cost tile ranges.  strips: (col, item, n-tile, tiles, cost per tile) in launch order; a tile goes to the CTA
+// its cumulative cost (at the tile's middle) falls into, so every CTA's total differs from total / nctas by less than one tile
+// and consecutive tiles of a strip stay together.  seg_off[c] .. seg_off[c+1] are CTA c's segments (a CTA the walk skips over
+// — a single tile dearer than a whole share — gets none).  Returns the number of segments.
+struct StageStrip {
+  int col, b, ntile, tiles;
+  long long cost;
+};
+int stage_partition(const StageStrip* strips, int n_strips, int nctas, int* seg_off, StageSeg* segs, int max_segs) {
+  long long total = 0;
+  for (int i = 0; i < n_strips; ++i) total += (long long)strips[i].tiles * strips[i].cost;
+  B2_CHECK(total > 0 && nctas >= 1, "stage partition: no work");
+  int nseg = 0, cur_cta = -1;
+  long long cum = 0;
+  for (int i = 0; i < n_strips; ++i) {
+    const StageStrip& st = strips[i];
+    bool open = false;
+    for (int t = 0; t < st.tiles; ++t) {
+      const int cta = (int)std::min<long long>(nctas - 1, (cum + st.cost / 2) * nctas / total);
+      cum += st.cost;
+      if (cta != cur_cta) {
+        for (int c = cur_cta + 1; c <= cta; ++c) seg_off[c] = nseg;
+        cur_cta = cta;
+        open = false;
+      }
+      if (!open) {
+        B2_CHECK(nseg < max_segs, "stage partition: too many segments");
+        segs[nseg].col = st.col; segs[nseg].b = st.b; segs[nseg].ntile = st.ntile; segs[nseg].t_begin = t; segs[nseg].t_end = t;
+        ++nseg;
+        open = true;
+      }
+      segs[nseg - 1].t_end = t + 1;
+    }
+  }
+  for (int c = cur_cta + 1; c <= nctas; ++c) seg_off[c] = nseg;
+  return nseg;
+}
+
 bool stage_umma_supported(const ConvParams* convs, int n_levels, int n_cols) {
   const int n = n_levels * n_cols;
   if (n < 1 || n > SG_MAX_CONVS) return false;
@@ -111,30 +149,12 @@ int launch_stage_umma(const ConvParams* convs, int n_levels, int n_cols, int bat
   memcpy(convs_t, convs, sizeof(ConvParams) * n);
   for (int lv = 0; lv < n_levels; ++lv)
     for (int j = 0; j < n_cols; ++j) dep_t[lv * n_cols + j] = lv > 0 ? (lv - 1) * n_cols + j : -1;
-  int nseg = 0, cur_cta = -1;
-  long long cum = 0;
+  std::vector<StageStrip> strips;
   for (int j = 0; j < n_cols; ++j)
     for (int b = 0; b < batch; ++b)
-      for (int nt = 0; nt < ntiles; ++nt) {
-        bool open = false;
-        for (int t = 0; t < mtl[b]; ++t) {
-          const int cta = (int)std::min<long long>(nctas - 1, (cum + wcol[j] / 2) * nctas / total);
-          cum += wcol[j];
-          if (cta != cur_cta) {
-            for (int c = cur_cta + 1; c <= cta; ++c) off_t[c] = nseg;  // (CTAs skipped over own no tiles)
-            cur_cta = cta;
-            open = false;
-          }
-          if (!open) {
-            B2_CHECK(nseg < 2048, "stage_umma: too many segments");
-            seg_t[nseg].col = j; seg_t[nseg].b = b; seg_t[nseg].ntile = nt; seg_t[nseg].t_begin = t; seg_t[nseg].t_end = t;
-            ++nseg;
-            open = true;
-          }
-          seg_t[nseg - 1].t_end = t + 1;
-        }
-      }
-  for (int c = cur_cta + 1; c <= nctas; ++c) off_t[c] = nseg;
+      for (int nt = 0; nt < ntiles; ++nt)
+        if (mtl[b] > 0) strips.push_back({j, b, nt, mtl[b], wcol[j]});
+  stage_partition(strips.data(), (int)strips.size(), nctas, off_t, seg_t, 2048);
   char* td = reinterpret_cast<char*>(tab_d);
   B2_CUDA(cudaMemcpyAsync(td, th, stage_umma_table_bytes(), cudaMemcpyHostToDevice, s));
   B2_CUDA(cudaMemsetAsync(flags_d, 0, sizeof(unsigned int) * (size_t)n * batch * tiles_max, s));
@@ -264,29 +284,11 @@ int launch_stage_pair(const ConvParams* c1, const ConvParams* c2, int n_levels, 
   memcpy(convs_t + n, c1, sizeof(ConvParams) * n);
   for (int lv = 0; lv < n_levels; ++lv)
     for (int j = 0; j < n_cols; ++j) dep_t[lv * n_cols + j] = lv > 0 ? (lv - 1) * n_cols + j : -1;
-  int nseg = 0, cur_cta = -1;
-  long long cum = 0;
+  std::vector<StageStrip> strips;
   for (int j = 0; j < n_cols; ++j)
-    for (int b = 0; b < batch; ++b) {
-      bool open = false;
-      for (int t = 0; t < mtl[(size_t)b * n_cols + j]; ++t) {
-        const int cta = (int)std::min<long long>(nctas - 1, (cum + wcol[j] / 2) * nctas / total);
-        cum += wcol[j];
-        if (cta != cur_cta) {
-          for (int c = cur_cta + 1; c <= cta; ++c) off_t[c] = nseg;
-          cur_cta = cta;
-          open = false;
-        }
-        if (!open) {
-          B2_CHECK(nseg < 2048, "stage_pair: too many segments");
-          seg_t[nseg].col = j; seg_t[nseg].b = b; seg_t[nseg].ntile = 0; seg_t[nseg].t_begin = t; seg_t[nseg].t_end = t;
-          ++nseg;
-          open = true;
-        }
-        seg_t[nseg - 1].t_end = t + 1;
-      }
-    }
-  for (int c = cur_cta + 1; c <= nctas; ++c) off_t[c] = nseg;
+    for (int b = 0; b < batch; ++b)
+      if (mtl[(size_t)b * n_cols + j] > 0) strips.push_back({j, b, 0, mtl[(size_t)b * n_cols + j], wcol[j]});
+  stage_partition(strips.data(), (int)strips.size(), nctas, off_t, seg_t, 2048);
   char* td = reinterpret_cast<char*>(tab_d);
   B2_CUDA(cudaMemcpyAsync(td, th, stage_umma_table_bytes(), cudaMemcpyHostToDevice, s));
   B2_CUDA(cudaMemsetAsync(flags_d, 0, sizeof(unsigned int) * (size_t)n * batch * tiles_max, s));
@@ -315,6 +317,29 @@ int launch_stage_pair(const ConvParams* c1, const ConvParams* c2, int n_levels, 
   B2_CUDA(le);
   B2_CUDA(cudaGetLastError());
   return 1;
+}
+
+// tests: cta_of_tile[k] = CTA of the k-th tile in strip order (strip i = column i, `strip_tiles[i]` tiles of `strip_cost[i]`)
+int stage_partition_debug(const int* strip_tiles, const long long* strip_cost, int n_strips, int nctas, int* cta_of_tile) {
+  B2_CHECK(strip_tiles && strip_cost && cta_of_tile && n_strips >= 1 && nctas >= 1 && nctas < 4096, "bad arguments");
+  std::vector<StageStrip> strips;
+  std::vector<long long> first(n_strips + 1, 0);
+  for (int i = 0; i < n_strips; ++i) {
+    B2_CHECK(strip_tiles[i] >= 0 && strip_cost[i] > 0, "bad strip");
+    strips.push_back({i, 0, 0, strip_tiles[i], strip_cost[i]});
+    first[i + 1] = first[i] + strip_tiles[i];
+  }
+  std::vector<int> off(nctas + 1, 0);
+  std::vector<StageSeg> segs((size_t)first[n_strips] + 1);
+  const int nseg = stage_partition(strips.data(), n_strips, nctas, off.data(), segs.data(), (int)segs.size());
+  for (long long k = 0; k < first[n_strips]; ++k) cta_of_tile[k] = -1;
+  for (int c = 0; c < nctas; ++c)
+    for (int q = off[c]; q < off[c + 1]; ++q)
+      for (int t = segs[q].t_begin; t < segs[q].t_end; ++t) {
+        B2_CHECK(cta_of_tile[first[segs[q].col] + t] == -1, "tile assigned twice");
+        cta_of_tile[first[segs[q].col] + t] = c;
+      }
+  return nseg;
 }
 
 }  // namespace b2

@@ -164,3 +164,41 @@ def test_pixel_shuffle_conv_equals_conv_transpose():
         y = F.conv1d(torch.from_numpy(x), torch.from_numpy(pack.pixel_shuffle_conv(w, u, k)), padding=1)[0].numpy()
         out = y.reshape(cout, u, L).transpose(0, 2, 1).reshape(cout, L * u)  # packed channel n = co*u + r
         assert np.abs(out - ref).max() < 1e-5
+
+
+def test_stage_partition_is_contiguous_and_balanced(built_library):
+    """Host logic of the per-stage HiFi-GAN kernels (stage_umma.cu: stage_partition): every tile goes to exactly one CTA, CTA
+    indices never decrease along the strips (contiguous ranges), and every CTA's modelled cost is within one tile of the mean —
+    for the bench shapes (3 branches x 251 tiles, costs of the 32-channel stage), a ragged batch and more CTAs than tiles."""
+    import ctypes as C
+
+    import numpy as np
+
+    from larynx_b200 import _lib
+
+    lib = _lib.load()
+
+    def run(tiles, cost, nctas):
+        tiles = np.asarray(tiles, np.int32)
+        cost = np.asarray(cost, np.int64)
+        out = np.full(int(tiles.sum()), -7, np.int32)
+        nr = C.c_int32(0)
+        rc = lib.b200tts_debug_stage_partition(tiles.ctypes.data, cost.ctypes.data, len(tiles), nctas, out.ctypes.data, C.byref(nr))
+        assert rc == 0, lib.b200tts_last_error()
+        return out, int(nr.value)
+
+    for tiles, cost, nctas in (([251, 251, 251], [3000, 3000, 3594], 148),
+                               ([5, 34, 12, 5, 34, 12, 5, 34, 12], [3600, 3600, 3600, 5088, 5088, 5088, 7584, 7584, 7584], 148),
+                               ([2, 1], [100, 900], 148), ([64, 64, 64, 64, 64, 64], [4464, 4464, 9456, 9456, 14448, 14448], 148)):
+        cta, n_ranges = run(tiles, cost, nctas)
+        assert cta.min() >= 0 and cta.max() < nctas
+        assert (np.diff(cta) >= 0).all()  # contiguous: the walk never goes back to an earlier CTA
+        per_tile = np.repeat(np.asarray(cost, np.int64), tiles)
+        load = np.bincount(cta, weights=per_tile, minlength=nctas)
+        used = min(nctas, int(np.sum(tiles)))
+        mean = per_tile.sum() / used
+        assert load.max() <= mean + per_tile.max() + 1, (load.max(), mean)
+        busy = load[load > 0]
+        if int(np.sum(tiles)) >= 4 * nctas:  # enough tiles per CTA for a meaningful lower bound
+            assert busy.min() >= mean - per_tile.max() - 1 and len(busy) == nctas
+        assert n_ranges >= len(busy) and n_ranges <= len(busy) + len(tiles)

@@ -8,6 +8,16 @@
 #include "kernels.cuh"
 #include "stage_umma.cuh"
 
+#ifndef SG_COST_A2
+#define SG_COST_A2 55  // ... of a 256 x 64 tile (x 1/2)
+#endif
+#ifndef SG_COST_AP
+#define SG_COST_AP 100  // ... of a ResBlock step (c1 + c2) on a 512 x 32 tile
+#endif
+#ifndef SG_COST_A1
+#define SG_COST_A1 26  // modelled cost (10 ns) of one (tap, 32-channel chunk) of a 128 x 128 tile
+#endif
+
 namespace b2 {
 
 void stage_umma_init_attributes() {
@@ -113,8 +123,8 @@ int launch_stage_umma(const ConvParams* convs, int n_levels, int n_cols, int bat
     for (int lv = 0; lv < n_levels; ++lv) {
       const long long kc = (long long)convs[lv * n_cols + j].K * nch;
       long long cost;
-      if (mt == 1) cost = std::max(26 * kc + 120, 600LL);
-      else if (mt == 2) cost = 55 * kc / 2 + 370;
+      if (mt == 1) cost = std::max((long long)SG_COST_A1 * kc + 120, 600LL);
+      else if (mt == 2) cost = (long long)SG_COST_A2 * kc / 2 + 370;
       else cost = std::max(50 * kc + 150, 600LL);
       wcol[j] += cost;
     }
@@ -251,7 +261,7 @@ int launch_stage_pair(const ConvParams* c1, const ConvParams* c2, int n_levels, 
   std::vector<int> S(n_cols);
   for (int j = 0; j < n_cols; ++j) {
     S[j] = mt * 128 - (c2[j].K - 1);
-    for (int lv = 0; lv < n_levels; ++lv) wcol[j] += std::max(100LL * c2[lv * n_cols + j].K * nch + 500, 550LL);
+    for (int lv = 0; lv < n_levels; ++lv) wcol[j] += std::max((long long)SG_COST_AP * c2[lv * n_cols + j].K * nch + 500, 550LL);
   }
   int tiles_max = 0;
   long long total = 0, n_tiles_all = 0;

@@ -45,9 +45,13 @@ struct StageParams {
 
 constexpr int SG_EW = 16;
 
+#ifndef SG_WST1
+#define SG_WST1 8  // weight ring slots (16 KB) of the 128-channel-tile variant
+#endif
+
 template <int MT>
 struct StageCfg {  // ring geometry per tile height (the persistent variants of conv_umma.cu)
-  static constexpr int WST = MT == 1 ? 8 : (MT == 2 ? 6 : 3);
+  static constexpr int WST = MT == 1 ? SG_WST1 : (MT == 2 ? 6 : 3);
   static constexpr int AST = 2;
   static constexpr int G = MT == 1 ? 1 : (MT == 2 ? 2 : 4);
   static constexpr int RA = MT * 128 + UM_HALO;
@@ -99,14 +103,14 @@ __global__ void __launch_bounds__(SG_EW * 32 + 128, 1) stage_umma_kernel(const _
   uint64_t* bars = reinterpret_cast<uint64_t*>(sW + WST * w_ring);
   uint64_t* a_full = bars;          // [AST]
   uint64_t* a_empty = bars + 2;     // [AST]
-  uint64_t* w_full = bars + 4;      // [WST <= 8]
-  uint64_t* w_empty = bars + 12;    // [WST <= 8]
-  uint64_t* acc_full = bars + 20;   // [2]
-  uint64_t* acc_empty = bars + 22;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
-  unsigned int* s_done = reinterpret_cast<unsigned int*>(bars + 25);  // epilogue warps that have finished an item (monotonic)
-  static_assert(WST <= 8 && AST == 2, "barrier slots");
-  float* s_bias_all = reinterpret_cast<float*>(bars + 26);  // [n_convs][Cout]
+  uint64_t* w_full = bars + 4;      // [WST <= 9]
+  uint64_t* w_empty = bars + 13;    // [WST <= 9]
+  uint64_t* acc_full = bars + 22;   // [2]
+  uint64_t* acc_empty = bars + 24;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
+  unsigned int* s_done = reinterpret_cast<unsigned int*>(bars + 27);  // epilogue warps that have finished an item (monotonic)
+  static_assert(WST <= 9 && AST == 2, "barrier slots");
+  float* s_bias_all = reinterpret_cast<float*>(bars + 28);  // [n_convs][Cout]
   const float *s_inv = nullptr, *s_anb = nullptr, *s_ans = nullptr;  // named by the (dead here) coupling branch of the epilogue text
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;

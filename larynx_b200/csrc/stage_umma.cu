@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "kernels.cuh"
@@ -31,11 +32,19 @@ static int stage_mt(int nt) { return nt <= 32 ? 4 : (nt <= 64 ? 2 : 1); }
 
 template <int MT>
 static int resident_ctas(size_t smem) {
+  // (per process: every GPU of a box is the same part; the query costs several microseconds per launch otherwise)
+  static std::mutex m;
+  static size_t last_smem = 0;
+  static int last = 0;
+  std::lock_guard<std::mutex> g(m);
+  if (last > 0 && last_smem == smem) return last;
   int dev = 0, sms = 0, per_sm = 0;
   B2_CUDA(cudaGetDevice(&dev));
   B2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   B2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stage_umma_kernel<MT>, SG_EW * 32 + 128, smem));
-  return sms * per_sm;
+  last_smem = smem;
+  last = sms * per_sm;
+  return last;
 }
 
 // Contiguous, equal-cost tile ranges.  strips: (col, item, n-tile, tiles, cost per tile) in launch order; a tile goes to the CTA
@@ -164,9 +173,10 @@ int launch_stage_umma(const ConvParams* convs, int n_levels, int n_cols, int bat
     for (int b = 0; b < batch; ++b)
       for (int nt = 0; nt < ntiles; ++nt)
         if (mtl[b] > 0) strips.push_back({j, b, nt, mtl[b], wcol[j]});
-  stage_partition(strips.data(), (int)strips.size(), nctas, off_t, seg_t, 2048);
+  const int nseg = stage_partition(strips.data(), (int)strips.size(), nctas, off_t, seg_t, 2048);
   char* td = reinterpret_cast<char*>(tab_d);
-  B2_CUDA(cudaMemcpyAsync(td, th, stage_umma_table_bytes(), cudaMemcpyHostToDevice, s));
+  // only the bytes in use: conv table + dep + offsets + the segments actually written (~10 of 52 KB)
+  B2_CUDA(cudaMemcpyAsync(td, th, (size_t)(reinterpret_cast<char*>(seg_t + nseg) - th), cudaMemcpyHostToDevice, s));
   B2_CUDA(cudaMemsetAsync(flags_d, 0, sizeof(unsigned int) * (size_t)n * batch * tiles_max, s));
   StageParams sp;
   sp.convs = reinterpret_cast<const ConvParams*>(td);
@@ -298,9 +308,10 @@ int launch_stage_pair(const ConvParams* c1, const ConvParams* c2, int n_levels, 
   for (int j = 0; j < n_cols; ++j)
     for (int b = 0; b < batch; ++b)
       if (mtl[(size_t)b * n_cols + j] > 0) strips.push_back({j, b, 0, mtl[(size_t)b * n_cols + j], wcol[j]});
-  stage_partition(strips.data(), (int)strips.size(), nctas, off_t, seg_t, 2048);
+  const int nseg = stage_partition(strips.data(), (int)strips.size(), nctas, off_t, seg_t, 2048);
   char* td = reinterpret_cast<char*>(tab_d);
-  B2_CUDA(cudaMemcpyAsync(td, th, stage_umma_table_bytes(), cudaMemcpyHostToDevice, s));
+  // only the bytes in use: conv table + dep + offsets + the segments actually written (~10 of 52 KB)
+  B2_CUDA(cudaMemcpyAsync(td, th, (size_t)(reinterpret_cast<char*>(seg_t + nseg) - th), cudaMemcpyHostToDevice, s));
   B2_CUDA(cudaMemsetAsync(flags_d, 0, sizeof(unsigned int) * (size_t)n * batch * tiles_max, s));
   StageParams sp;
   sp.convs = reinterpret_cast<const ConvParams*>(td);

@@ -89,6 +89,14 @@ int b200tts_glow_encode(const b200tts_glow* m, b200tts_call* call, const int64_t
 int b200tts_glow_decode(const b200tts_glow* m, b200tts_call* call, float noise_scale, const float* eps, int eps_ld,
                         uint64_t seed, float* mel_out, int mel_ld);
 
+/* Reduced-precision encoder (BASELINE config 3; the reference's counterpart is `half=True`, which casts the whole
+ * PyTorch model to fp16: larynx/glow_tts.py:90-91).  on != 0: every following b200tts_glow_encode on this call multiplies
+ * the prenet, q/k/v/o, attention and FFN GEMMs on bf16-rounded activations (one operand plane instead of three; fp32
+ * accumulation, fp32 LayerNorm / softmax, weights at full split precision) when the batch takes the single-launch
+ * encoder (max_tx <= 128); proj_m, the duration predictor, the flow decoder and the vocoder are unchanged.  Alignments
+ * can differ from the fp32 result in this mode — tools/half_report.py measures how often.  Default 0. */
+int b200tts_call_set_encoder_bf16(b200tts_call* call, int on);
+
 /* Debug/parity taps of the last encode on this call (any pointer may be NULL):
  * logw [batch][max_tx] f32, w_ceil [batch][max_tx] i32, idx [batch][idx_ld] i32 (phoneme index
  * each frame copies, -1 beyond y_len) — "alignment indices bit-exact" is checked on these. */

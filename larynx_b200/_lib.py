@@ -61,6 +61,7 @@ _SIGNATURES = {
     "b200tts_call_stream": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "b200tts_call_set_debug": (C.c_int, [C.c_void_p, C.c_int]),
     "b200tts_call_set_denoiser": (C.c_int, [C.c_void_p, C.c_float]),
+    "b200tts_call_set_encoder_bf16": (C.c_int, [C.c_void_p, C.c_int]),
     "b200tts_glow_create": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]),
     "b200tts_glow_destroy": (C.c_int, [C.c_void_p]),
     "b200tts_glow_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),

@@ -40,6 +40,7 @@ int launch_enc_chain(const EncStep* steps, const EncChainParams& fp, int max_tx,
         const EncConvOp& o = st.conv[j];
         const int nch = (o.Cin + UM_BKC - 1) / UM_BKC;
         B2_CHECK(o.w && o.xp && (o.y || o.yp), "enc_chain: conv without operands");
+        B2_CHECK(o.planes == 1 || o.planes == 3, "enc_chain: 1 or 3 activation planes");
         B2_CHECK(o.NT >= 16 && o.NT <= EC_NT_MAX && o.NT % 16 == 0, "enc_chain: bad N tile");
         B2_CHECK(o.K >= 1 && o.K - 1 <= EC_HALO && o.pad <= UM_PADL, "enc_chain: receptive field too wide");
         B2_CHECK(o.ksplit >= 1 && nch % o.ksplit == 0, "enc_chain: K-split must divide the input chunks");
@@ -55,7 +56,8 @@ int launch_enc_chain(const EncStep* steps, const EncChainParams& fp, int max_tx,
     } else {
       const EncAttnOp& a = st.att;
       B2_CHECK(st.type == ES_ATTN && a.H % a.n_heads == 0 && a.H / a.n_heads == EA_DK && a.window <= 4 &&
-                   a.y0 + a.n_heads <= EC_YT && a.relk_img && a.relv_img, "enc_chain: unsupported attention");
+                   a.y0 + a.n_heads <= EC_YT && a.relk_img && a.relv_img && (a.planes == 1 || a.planes == 3),
+               "enc_chain: unsupported attention");
     }
   }
   const int groups = std::max(1, std::min(fp.batch, enc_resident_ctas() / (m_tiles * EC_YT)));

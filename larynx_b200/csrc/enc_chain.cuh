@@ -259,9 +259,10 @@ __global__ void __launch_bounds__(EC_THREADS, 1) enc_chain_kernel(const __grid_c
               if (sq >= EC_AST) { sq -= EC_AST; pq ^= 1; }
               if (q < 2 && c0 + q < per) {
                 mbar_wait(&a_empty[sq], pq);
-                if (j == 0) mbar_arrive_expect_tx(&a_full[sq], NSPLIT * UM_KCH * kc_bytes);
+                if (j == 0) mbar_arrive_expect_tx(&a_full[sq], op->planes * UM_KCH * kc_bytes);
                 const int sp = j >> 2, kc = j & 3;
-                bulk_g2s(sA + (size_t)sq * a_stage + sp * a_split_bytes + kc * RA * 16,
+                if (sp < op->planes)  // bf16-activation mode reads the hi plane only
+                  bulk_g2s(sA + (size_t)sq * a_stage + sp * a_split_bytes + kc * RA * 16,
                          xp + (((size_t)sp * op->xp_kc + c * UM_KCH + kc) * fp.rows + row0) * 16, kc_bytes, &a_full[sq]);
               }
               as += min(2, per - c0);
@@ -285,9 +286,9 @@ __global__ void __launch_bounds__(EC_THREADS, 1) enc_chain_kernel(const __grid_c
             unsigned char* sK = smem_raw + EA_NS * EA_QPLANE;
             unsigned char* sV = smem_raw;
             // phase 1: Q rows [0,128) and K' = [K rows [0,128); Ek rows] (image rows >= len are zero)
-            if (lane == 0) mbar_arrive_expect_tx(at_qk, EA_NS * (EA_QPLANE + EA_XPLANE));
+            if (lane == 0) mbar_arrive_expect_tx(at_qk, at.planes * (EA_QPLANE + EA_XPLANE));
             __syncwarp();
-            for (int i = lane; i < EA_NS * EA_KC; i += 32) {
+            for (int i = lane; i < at.planes * EA_KC; i += 32) {
               const int sp = i / EA_KC, kc = i - sp * EA_KC;
               bulk_g2s(sQ + sp * EA_QPLANE + kc * EA_ROWS * 16, img(0, sp, kc), EA_ROWS * 16, at_qk);
               bulk_g2s(sK + sp * EA_XPLANE + kc * EA_XR * 16, img(1, sp, kc), EA_ROWS * 16, at_qk);
@@ -295,9 +296,9 @@ __global__ void __launch_bounds__(EC_THREADS, 1) enc_chain_kernel(const __grid_c
             }
             // phase 2: V' = [V; Ev] over the dead Q / K' bytes, as soon as the S MMAs have retired
             mbar_wait(at_s, att_use & 1);
-            if (lane == 0) mbar_arrive_expect_tx(at_v, EA_NS * EA_XPLANE);
+            if (lane == 0) mbar_arrive_expect_tx(at_v, at.planes * EA_XPLANE);
             __syncwarp();
-            for (int i = lane; i < EA_NS * EA_KC; i += 32) {
+            for (int i = lane; i < at.planes * EA_KC; i += 32) {
               const int sp = i / EA_KC, kc = i - sp * EA_KC;
               bulk_g2s(sV + sp * EA_XPLANE + kc * EA_XR * 16, img(2, sp, kc), EA_ROWS * 16, at_v);
               bulk_g2s(sV + sp * EA_XPLANE + kc * EA_XR * 16 + EA_ROWS * 16, at.relv_img + ((size_t)sp * EA_KC + kc) * 256, 256, at_v);
@@ -352,8 +353,10 @@ __global__ void __launch_bounds__(EC_THREADS, 1) enc_chain_kernel(const __grid_c
                   const uint64_t a0 = a_k + ks2 * a_ks, b0 = b_k + ks2 * b_ks;
                   const uint32_t acc0 = (i == 0 && ks2 == 0) ? 0u : 1u;
                   mma_bf16_ss(tmem, a0, b0, idesc3, acc0);                     // hi  x [hi|lo|lo2] -> [c0|c1|c2]
-                  mma_bf16_ss(tmem + NT, a0 + a_sp, b0, idesc2, 1u);           // lo  x [hi|lo]     -> [c1|c2]
-                  mma_bf16_ss(tmem + 2 * NT, a0 + 2 * a_sp, b0, idesc1, 1u);   // lo2 x hi          -> c2
+                  if (op->planes == 3) {
+                    mma_bf16_ss(tmem + NT, a0 + a_sp, b0, idesc2, 1u);         // lo  x [hi|lo]     -> [c1|c2]
+                    mma_bf16_ss(tmem + 2 * NT, a0 + 2 * a_sp, b0, idesc1, 1u); // lo2 x hi          -> c2
+                  }
                 }
                 if (k == K - 1) mma_commit(&a_empty[as]);
                 if (j == cnt - 1) mma_commit(&w_empty[ws]);
@@ -385,12 +388,14 @@ __global__ void __launch_bounds__(EC_THREADS, 1) enc_chain_kernel(const __grid_c
             for (int k = 0; k < EA_DK / 16; ++k) {
               const uint64_t a = qd + k * qks, bb = kd + k * kks;
               const uint32_t acc = k ? 1u : 0u;
-              mma_bf16_ss(tS, a + qsp, bb + ksp, idS, acc);     // lo*lo
-              mma_bf16_ss(tS, a, bb + 2 * ksp, idS, 1u);        // hi*lo2
-              mma_bf16_ss(tS, a + 2 * qsp, bb, idS, 1u);        // lo2*hi
-              mma_bf16_ss(tS, a, bb + ksp, idS, 1u);            // hi*lo
-              mma_bf16_ss(tS, a + qsp, bb, idS, 1u);            // lo*hi
-              mma_bf16_ss(tS, a, bb, idS, 1u);                  // hi*hi
+              if (st.att.planes == 3) {
+                mma_bf16_ss(tS, a + qsp, bb + ksp, idS, acc);     // lo*lo
+                mma_bf16_ss(tS, a, bb + 2 * ksp, idS, 1u);        // hi*lo2
+                mma_bf16_ss(tS, a + 2 * qsp, bb, idS, 1u);        // lo2*hi
+                mma_bf16_ss(tS, a, bb + ksp, idS, 1u);            // hi*lo
+                mma_bf16_ss(tS, a + qsp, bb, idS, 1u);            // lo*hi
+              }
+              mma_bf16_ss(tS, a, bb, idS, st.att.planes == 3 ? 1u : acc);  // hi*hi
             }
             mma_commit(at_s);
           }
@@ -409,12 +414,14 @@ __global__ void __launch_bounds__(EC_THREADS, 1) enc_chain_kernel(const __grid_c
             for (int k = 0; k < EA_XR / 16; ++k) {
               const uint64_t a = pd + k * pks, bb = vd + k * vks;
               const uint32_t acc = k ? 1u : 0u;
-              mma_bf16_ss(tO, a + psp, bb + vsp, idO, acc);
-              mma_bf16_ss(tO, a, bb + 2 * vsp, idO, 1u);
-              mma_bf16_ss(tO, a + 2 * psp, bb, idO, 1u);
-              mma_bf16_ss(tO, a, bb + vsp, idO, 1u);
-              mma_bf16_ss(tO, a + psp, bb, idO, 1u);
-              mma_bf16_ss(tO, a, bb, idO, 1u);
+              if (st.att.planes == 3) {
+                mma_bf16_ss(tO, a + psp, bb + vsp, idO, acc);
+                mma_bf16_ss(tO, a, bb + 2 * vsp, idO, 1u);
+                mma_bf16_ss(tO, a + 2 * psp, bb, idO, 1u);
+                mma_bf16_ss(tO, a, bb + vsp, idO, 1u);
+                mma_bf16_ss(tO, a + psp, bb, idO, 1u);
+              }
+              mma_bf16_ss(tO, a, bb, idO, st.att.planes == 3 ? 1u : acc);
             }
             mma_commit(at_o);
           }

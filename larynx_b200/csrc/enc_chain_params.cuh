@@ -14,6 +14,7 @@ struct EncConvOp {
   const void* w;         // weight image (pack.umma_image, nsplit 3)
   const float* bias;     // added in the epilogue; nullptr: raw sums (K-split partials, the following reduce step adds it)
   int Cin, Cout, K, pad, NT, ntiles, ksplit, y0, act;
+  int planes;            // activation planes multiplied: 3 = fp32-grade (hi, lo, lo2), 1 = bf16 activations (`half` mode)
   const unsigned char* xp;  // input operand image
   long long xp_bs;
   int xp_kc;
@@ -50,6 +51,7 @@ struct EncAttnOp {
   int qkv_kc;
   const unsigned char *relk_img, *relv_img;
   int window, H, n_heads, y0;
+  int planes;            // 3: all six split products of Q K'^T and P' V'; 1: bf16 operands (hi x hi only)
   unsigned char* out_p;
   long long out_bs;
   int out_kc;

@@ -225,6 +225,7 @@ struct b200tts_call {
   float last_ms = 0.f;
   int debug = 0;
   float denoise = 0.f;  // denoiser strength applied after the vocoder (0 = off)           larynx/hifi_gan.py:152-166
+  int enc_bf16 = 0;     // 1: text-encoder GEMMs on bf16 activations (b200tts_call_set_encoder_bf16)
   Arena enc, dec, voc, stg;
   // state carried from encode to decode
   const b200tts_glow* enc_model = nullptr;
@@ -580,17 +581,18 @@ static void glow_encode_impl(const b200tts_glow* m, b200tts_call* c, const int64
     int ns = 0;
     const long long part_stride = (long long)B * part_c * ld;  // floats between K-split partial buffers
     auto img = [](const Planes& pl) { return (unsigned char*)pl.ptr; };
+    int planes = c->enc_bf16 ? 1 : 3;  // activation planes of the prenet / encoder-layer GEMMs; the duration head keeps 3
     // conv -> raw fp32 partials (K-split `ksplit`) at CTA rows y0..
     auto conv_partial = [&](EncConvOp& o, const ConvW& w, const Planes& in, int pad, int ksplit, int y0) {
       o.w = w.wu; o.bias = nullptr; o.Cin = w.cin; o.Cout = w.cout; o.K = w.k; o.pad = pad; o.NT = w.nt;
-      o.ntiles = (w.cout + w.nt - 1) / w.nt; o.ksplit = ksplit; o.y0 = y0; o.act = ACT_NONE;
+      o.ntiles = (w.cout + w.nt - 1) / w.nt; o.ksplit = ksplit; o.y0 = y0; o.act = ACT_NONE; o.planes = planes;
       o.xp = img(in); o.xp_bs = in.bs; o.xp_kc = in.kc;
       o.y = PART; o.y_bs = (long long)part_c * ld; o.part_stride = part_stride; o.y_ld = ld;
     };
     // conv -> operand image (+ bias, activation)
     auto conv_image = [&](EncConvOp& o, const ConvW& w, const Planes& in, int pad, int act, const Planes& out, int y0) {
       o.w = w.wu; o.bias = w.b; o.Cin = w.cin; o.Cout = w.cout; o.K = w.k; o.pad = pad; o.NT = w.nt;
-      o.ntiles = (w.cout + w.nt - 1) / w.nt; o.ksplit = 1; o.y0 = y0; o.act = act;
+      o.ntiles = (w.cout + w.nt - 1) / w.nt; o.ksplit = 1; o.y0 = y0; o.act = act; o.planes = planes;
       o.xp = img(in); o.xp_bs = in.bs; o.xp_kc = in.kc;
       o.yp = img(out); o.yp_bs = out.bs; o.yp_kc = out.kc;
     };
@@ -631,7 +633,7 @@ static void glow_encode_impl(const b200tts_glow* m, b200tts_call* c, const int64
         EncAttnOp& a = e.att;
         a.qkv_p = img(QKV_p); a.qkv_bs = QKV_p.bs; a.qkv_kc = QKV_p.kc;
         a.relk_img = (const unsigned char*)L.relk_img; a.relv_img = (const unsigned char*)L.relv_img;
-        a.window = m->window; a.H = H; a.n_heads = m->n_heads; a.y0 = 0;
+        a.window = m->window; a.H = H; a.n_heads = m->n_heads; a.y0 = 0; a.planes = planes;
         a.out_p = img(ATT_p); a.out_bs = ATT_p.bs; a.out_kc = ATT_p.kc;
       }
       {
@@ -653,13 +655,14 @@ static void glow_encode_impl(const b200tts_glow* m, b200tts_call* c, const int64
       }
     }
     // proj_m and the duration predictor                                        models.py:133, 39-49
+    planes = 3;  // fp32-grade whatever the mode: the durations decide the alignment
     {
       EncStep& e = st[ns++];
       e.type = ES_CONV; e.n_conv = 2;
       conv_partial(e.conv[0], m->dp1, X_p, m->K / 2, 2, 0);
       EncConvOp& pm = e.conv[1];
       pm.w = m->proj_m.wu; pm.bias = m->proj_m.b; pm.Cin = H; pm.Cout = mel; pm.K = 1; pm.pad = 0; pm.NT = m->proj_m.nt;
-      pm.ntiles = (mel + pm.NT - 1) / pm.NT; pm.ksplit = 1; pm.y0 = e.conv[0].ntiles * 2; pm.act = ACT_NONE;
+      pm.ntiles = (mel + pm.NT - 1) / pm.NT; pm.ksplit = 1; pm.y0 = e.conv[0].ntiles * 2; pm.act = ACT_NONE; pm.planes = 3;
       pm.xp = img(X_p); pm.xp_bs = X_p.bs; pm.xp_kc = X_p.kc;
       pm.y = c->xm_d; pm.y_bs = (long long)mel * ld; pm.y_ld = ld;
       reduce(2, Fd, m->dp1.b, nullptr, m->dp_ln1g, m->dp_ln1b, 1, 0, nullptr, &D1_p);
@@ -1808,6 +1811,13 @@ int b200tts_call_set_denoiser(b200tts_call* call, float strength) {
   B2_CHECK(call, "null argument");
   B2_CHECK(strength == strength, "denoiser strength is NaN");
   call->denoise = strength > 0.f ? strength : 0.f;
+  B2_API_END
+}
+
+int b200tts_call_set_encoder_bf16(b200tts_call* call, int on) {
+  B2_API_BEGIN
+  B2_CHECK(call, "null argument");
+  call->enc_bf16 = on ? 1 : 0;
   B2_API_END
 }
 

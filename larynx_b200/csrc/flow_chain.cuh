@@ -29,11 +29,20 @@ constexpr int FC_NT = 64;      // N tile of start / in / res_skip (pack.py: B200
 constexpr int FC_YT = 6;       // channel-tile CTAs per time tile = 2 * Hd / FC_NT
 constexpr int FC_EW = 8;       // epilogue warps
 constexpr int FC_KMAX = 5;     // taps of an in_layer (bounded so that the geometry check is explicit)
-constexpr int FC_G1 = 3;       // 1x1 convs: 32-channel chunks per weight slot
-constexpr int FC_WST = 3;      // weight ring slots of FC_KMAX blocks (40 KB): one chunk with all its taps (in_layer) or FC_G1
+#ifndef FC_G1_V
+#define FC_G1_V 3
+#endif
+#ifndef FC_WST_V
+#define FC_WST_V 3
+#endif
+#ifndef FC_AST_V
+#define FC_AST_V 4
+#endif
+constexpr int FC_G1 = FC_G1_V;  // 1x1 convs: 32-channel chunks per weight slot
+constexpr int FC_WST = FC_WST_V;  // weight ring slots of FC_KMAX blocks (40 KB): one chunk with all its taps (in_layer) or FC_G1
                                // chunks of a 1x1 conv.  Per slot the MMA warp pays one wait and one commit; with one block
                                // per slot that fixed cost (~150 clk) exceeded the 4 MMAs it paid for (measured: 6.9 vs 4.8 us)
-constexpr int FC_AST = 4;
+constexpr int FC_AST = FC_AST_V;
 constexpr int FC_HALO = 16;    // max (K-1)*dil
 constexpr int FC_RA = 128 + FC_HALO;
 constexpr int FC_THREADS = FC_EW * 32 + 96;
@@ -269,13 +278,13 @@ __global__ void __launch_bounds__(FC_THREADS, 1) flow_chain_kernel(const __grid_
               const uint32_t roff = a_row_off(row0u);
               const long long row0 = row0u - roff;
               const uint32_t kc_bytes = (uint32_t)((128 + (st.K - 1) * st.dil + (int)roff + 7) & ~7) * 16;
-              static_assert(FC_AST == 4 && NSPLIT * UM_KCH == 8, "lane -> (stage, copy) mapping");
+              static_assert(FC_AST >= 1 && FC_AST <= 4 && NSPLIT * UM_KCH == 8, "lane -> (stage, copy) mapping");
               for (int c0 = 0; c0 < st.nch; c0 += FC_AST) {
                 const int c = c0 + q;
                 int sq = as + q;
                 uint32_t pq = aph;
                 if (sq >= FC_AST) { sq -= FC_AST; pq ^= 1; }
-                if (c < st.nch) {
+                if (q < FC_AST && c < st.nch) {
                   mbar_wait(&a_empty[sq], pq);
                   if (j == 0) mbar_arrive_expect_tx(&a_full[sq], NSPLIT * UM_KCH * kc_bytes);
                   const int sp = j >> 2, kc = j & 3;

@@ -62,6 +62,10 @@ class Call:
         check(_lib.load().b200tts_debug_noise(self._h, int(seed) & (2**64 - 1), batch, mel, n, ptr(out), out.shape[2]))
         return out[:, :, :n]
 
+    def set_encoder_bf16(self, on: bool):
+        """Reduced-precision text encoder for the following encode calls on this context (b200tts.h; default off)."""
+        check(_lib.load().b200tts_call_set_encoder_bf16(self._h, int(bool(on))))
+
     def set_denoiser(self, strength: float):
         """Denoiser strength of the following vocoder calls on this context (0 = off; larynx/hifi_gan.py:152-166)."""
         check(_lib.load().b200tts_call_set_denoiser(self._h, float(strength)))
@@ -120,9 +124,11 @@ class GlowModel:
         except Exception:  # noqa: BLE001
             pass
 
-    def encode(self, call: Call, ids, x_len, batch: int, max_tx: int, length_scale: float = 1.0) -> np.ndarray:
+    def encode(self, call: Call, ids, x_len, batch: int, max_tx: int, length_scale: float = 1.0,
+               encoder_bf16: bool = False) -> np.ndarray:
         """Phase A.  ids [batch, max_tx] int64, x_len [batch] int32 (numpy or device tensors)."""
         y_len = np.zeros(batch, dtype=np.int32)
+        call.set_encoder_bf16(encoder_bf16)
         check(_lib.load().b200tts_glow_encode(self._h, call._h, ptr(ids), ptr(x_len), batch, max_tx, float(length_scale), ptr(y_len)))
         return y_len
 

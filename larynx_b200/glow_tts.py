@@ -4,7 +4,11 @@ Same constructor (a TextToSpeechModelConfig whose model_path holds `generator.pt
 same `phonemes_to_mels(phoneme_ids, settings)` contract: int64 ids [T_x] in, float32 mel
 [1, 80, T_y] numpy array out (what the ONNX backend returns, larynx/glow_tts.py:161-170), same
 settings keys (`noise_scale` 0.667, `length_scale` 1.0; larynx/glow_tts.py:104-121).
-Extra, optional settings: `eps` (injected N(0,1) noise [80, >=T_y], for parity tests) and `seed`.
+Extra, optional settings: `eps` (injected N(0,1) noise [80, >=T_y], for parity tests), `seed`, and `encoder_bf16`
+(default: the instance's `encoder_bf16`, False) — the reduced-precision text encoder of BASELINE config 3.  `config.half`
+is accepted and does NOT switch it on: it only acts on the reference's PyTorch-CUDA backend (larynx/glow_tts.py:90-91;
+the ONNX backend this drop-in is measured against ignores it, :96-100) and larynx.load_tts_model defaults it to True
+(larynx/__init__.py:298), so honouring it would silently drop every stock caller below the 1e-3 contract.
 """
 from __future__ import annotations
 
@@ -50,6 +54,7 @@ class GlowTextToSpeech(TextToSpeechModel):
         self.model = GlowModel(blob, self.device)
         self.noise_scale = 0.667
         self.length_scale = 1.0
+        self.encoder_bf16 = False  # opt-in: bf16 activations in the encoder GEMMs (alignments may differ; tools/half_report.py)
         self._seed_base = fresh_seed()  # per instance (process, rank, model): default noise never repeats across them
         self._seed_lock = threading.Lock()
         self._seed_next = 0
@@ -60,7 +65,9 @@ class GlowTextToSpeech(TextToSpeechModel):
         noise_scale, length_scale = self.noise_scale, self.length_scale
         eps = None
         seed = None
+        bf16 = self.encoder_bf16
         if settings:
+            bf16 = bool(settings.get("encoder_bf16", bf16))
             noise_scale = float(settings.get("noise_scale", noise_scale))
             length_scale = float(settings.get("length_scale", length_scale))
             if settings.get("speaker_id") is not None:
@@ -73,7 +80,7 @@ class GlowTextToSpeech(TextToSpeechModel):
         check_ids(ids, self.model.num_symbols)
         x_len = np.array([ids.shape[1]], dtype=np.int32)
         call = CALLS.get(self.device)
-        y_len = self.model.encode(call, ids, x_len, 1, ids.shape[1], length_scale)
+        y_len = self.model.encode(call, ids, x_len, 1, ids.shape[1], length_scale, encoder_bf16=bf16)
         t_y = int(y_len[0])
         mel = np.zeros((1, self.model.mel_channels, t_y), dtype=np.float32)
         if t_y == 0:

@@ -96,7 +96,7 @@ def synthesize_batch(tts_model, vocoder_model, glue: MelGlue, id_rows: Sequence[
     ids, x_len = engine.pad_ids(id_rows)
     engine.check_ids(ids, g.num_symbols)
     b = len(id_rows)
-    y_len = g.encode(call, ids, x_len, b, ids.shape[1], length_scale)
+    y_len = g.encode(call, ids, x_len, b, ids.shape[1], length_scale, encoder_bf16=bool(getattr(tts_model, "encoder_bf16", False)))
     ty = int(y_len.max()) if b else 0
     n = ty * v.hop
     pcm_i16 = np.zeros((b, max(n, 1)), dtype=np.int16)

@@ -558,6 +558,43 @@ np.savez(sys.argv[1], one=one, many=many)
     assert not many[1, 47 * 256:].any()  # nothing behind an item's length
 
 
+def test_encoder_bf16_mode_is_opt_in_bounded_and_resets():
+    """BASELINE config 3's reduced-precision encoder (b200tts_call_set_encoder_bf16): off unless asked for, a small bounded
+    drift of logw / mel when on (bf16 activations in the encoder GEMMs, fp32 duration head), and switching it off again
+    restores the default arithmetic bit for bit.  tools/half_report.py measures the alignment mismatch rate."""
+    g = np.load(os.path.join(GOLDEN, "bench128.npz"))
+    glow = common.product_glow()
+    call = engine.CALLS.get(0)
+    ids = g["ids"]
+    eps = synth.seeded_eps(4096, seed=int(g["eps_seed"]))
+    st = {"noise_scale": float(g["noise_scale"]), "length_scale": float(g["length_scale"]), "eps": eps}
+
+    def run(**extra):
+        mel = glow.phonemes_to_mels(ids, dict(st, **extra))
+        logw, w_ceil, _ = glow.model.alignment(call, 1, len(ids), mel.shape[2])
+        return mel, logw[0].copy(), w_ceil[0].copy()
+
+    mel0, logw0, w0 = run()
+    assert np.array_equal(w0, g["w_ceil"])
+    mel1, logw1, w1 = run(encoder_bf16=True)
+    d = float(np.abs(logw1 - logw0).max())
+    print("encoder_bf16: max|dlogw| %.3e, w_ceil mismatches %d / %d" % (d, int((w1 != w0).sum()), len(ids)))
+    assert 0.0 < d < 0.1  # the mode really changes the arithmetic, and only by bf16 rounding
+    assert int((w1 != w0).sum()) <= len(ids) // 4
+    if np.array_equal(w1, w0):
+        assert float(np.abs(mel1 - mel0).max()) < 0.1
+    mel2, logw2, w2 = run()  # the default again
+    assert np.array_equal(logw2, logw0) and np.array_equal(mel2, mel0)
+    glow.encoder_bf16 = True  # instance default, overridable per call
+    try:
+        _, logw3, _ = run()
+        assert np.array_equal(logw3, logw1)
+        _, logw4, _ = run(encoder_bf16=False)
+        assert np.array_equal(logw4, logw0)
+    finally:
+        glow.encoder_bf16 = False
+
+
 def test_device_resident_buffers():
     """`value` in bench.py is measured with inputs/outputs resident in HBM: same results as host buffers."""
     glow, voc = common.product_glow(), common.product_hifi()

@@ -83,7 +83,8 @@ def _install_fakes(monkeypatch, loaded):
             return port.glow_forward(self.sd, self.cfg, torch.from_numpy(ids), torch.from_numpy(xl.astype(np.int64)), noise, ls,
                                      None if eps is None else torch.from_numpy(eps).unsqueeze(0))
 
-        def encode(self, call, ids, x_len, batch, max_tx, length_scale=1.0):
+        def encode(self, call, ids, x_len, batch, max_tx, length_scale=1.0, encoder_bf16=False):
+            assert not encoder_bf16, "the stock factories must get the full-precision encoder (config.half is not honoured)"
             call.enc = (np.array(ids), np.array(x_len), float(length_scale))
             r = self._run(call, 0.0, None)
             return np.array([r["mel"].shape[2]], dtype=np.int32)

@@ -360,7 +360,7 @@ void launch_rel_attention(const float* qkv, long long bs, int ld, int H, int n_h
 //   idx[f] = phoneme whose span [cum[i-1], cum[i]) contains frame f  (f < y_len), else -1
 // one block per batch item.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) duration_kernel(const float* __restrict__ h, long long h_bs, int h_ld, int C,
+__global__ void __launch_bounds__(256) duration_generic_kernel(const float* __restrict__ h, long long h_bs, int h_ld, int C,
                                                        const float* __restrict__ pw, const float* __restrict__ pb,
                                                        const int* __restrict__ lens, int max_tx, float length_scale,
                                                        int n_sqz, float* __restrict__ logw, int* __restrict__ w_ceil,
@@ -419,11 +419,94 @@ __global__ void __launch_bounds__(256) duration_kernel(const float* __restrict__
   }
 }
 
+// C % 4 == 0, C <= 256 (every reference voice: filter_channels_dp = 256).  Four threads per phoneme load a quarter of the
+// channels each — all loads of the block are in flight together, one L2 round trip instead of one per 32 channels — and
+// then hand the fma chain from quarter to quarter, so the sum keeps the plain channel order of the generic kernel
+// (bit-identical logw).  The scan is a warp scan per 32 phonemes + warp totals.
+constexpr int DUR_PH = 128;  // phonemes per pass
+__global__ void __launch_bounds__(DUR_PH * 4) duration_kernel(const float* __restrict__ h, long long h_bs, int h_ld, int C,
+                                                              const float* __restrict__ pw, const float* __restrict__ pb,
+                                                              const int* __restrict__ lens, int max_tx, float length_scale,
+                                                              int n_sqz, float* __restrict__ logw, int* __restrict__ w_ceil,
+                                                              int* __restrict__ cum, int* __restrict__ y_len) {
+  __shared__ int s_wc[DUR_PH];
+  __shared__ int s_wtot[DUR_PH / 32];
+  __shared__ int s_carry;
+  const int b = blockIdx.x, len = lens[b];
+  const int tid = threadIdx.x, lane = tid & 31, tl = tid >> 2, q = tid & 3;
+  const float* hb = h + (size_t)b * h_bs;
+  const int cq = C >> 2;
+  if (tid == 0) s_carry = 0;
+  for (int t0 = 0; t0 < max_tx; t0 += DUR_PH) {
+    const int t = t0 + tl;
+    const bool on = t < max_tx && t < len;
+    float x[64];
+    if (on) {
+#pragma unroll
+      for (int j = 0; j < 64; ++j)
+        if (j < cq) x[j] = __ldcg(hb + (size_t)(q * cq + j) * h_ld + t);
+    }
+    float a = 0.f;
+#pragma unroll
+    for (int qq = 0; qq < 4; ++qq) {
+      if (on && q == qq) {
+#pragma unroll
+        for (int j = 0; j < 64; ++j)
+          if (j < cq) a = fmaf(pw[qq * cq + j], x[j], a);
+      }
+      a = __shfl_sync(0xffffffffu, a, (lane & ~3) | qq);  // the chain value after quarter qq, to the whole quad
+    }
+    if (q == 0) {
+      int wc = 0;
+      float lw = 0.f;
+      if (on) {
+        lw = a + pb[0];
+        wc = (int)ceilf(expf(lw) * length_scale);
+      }
+      if (t < max_tx) {
+        logw[(size_t)b * max_tx + t] = lw;
+        w_ceil[(size_t)b * max_tx + t] = wc;
+      }
+      s_wc[tl] = wc;
+    }
+    __syncthreads();
+    int incl = 0;
+    if (tid < DUR_PH) {
+      incl = s_wc[tid];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += n;
+      }
+      if (lane == 31) s_wtot[tid >> 5] = incl;
+    }
+    __syncthreads();
+    if (tid < DUR_PH) {
+      int off = s_carry;
+      for (int w = 0; w < (tid >> 5); ++w) off += s_wtot[w];
+      incl += off;
+      if (t0 + tid < max_tx) cum[(size_t)b * max_tx + t0 + tid] = incl;
+    }
+    __syncthreads();
+    if (tid == DUR_PH - 1) s_carry = incl;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int total = s_carry;
+    if (total < 1) total = 1;
+    y_len[b] = (total / n_sqz) * n_sqz;
+  }
+}
+
 void launch_duration(const float* h, long long h_bs, int h_ld, int C, const float* pw, const float* pb,
                      const int* lens, int batch, int max_tx, float length_scale, int n_sqz, float* logw, int* w_ceil,
                      int* cum, int* y_len, cudaStream_t s) {
-  duration_kernel<<<batch, 256, 0, s>>>(h, h_bs, h_ld, C, pw, pb, lens, max_tx, length_scale, n_sqz, logw, w_ceil,
-                                        cum, y_len);
+  if (C % 4 == 0 && C <= 256)
+    duration_kernel<<<batch, DUR_PH * 4, 0, s>>>(h, h_bs, h_ld, C, pw, pb, lens, max_tx, length_scale, n_sqz, logw, w_ceil, cum,
+                                                 y_len);
+  else
+    duration_generic_kernel<<<batch, 256, 0, s>>>(h, h_bs, h_ld, C, pw, pb, lens, max_tx, length_scale, n_sqz, logw, w_ceil,
+                                                  cum, y_len);
   B2_CUDA(cudaGetLastError());
 }
 
@@ -600,19 +683,31 @@ __global__ void __launch_bounds__(POST_BT) conv_post_kernel(const float* __restr
   const float* a1 = x1 + (size_t)b * bs;
   const float* a2 = x2 ? x2 + (size_t)b * bs : nullptr;
   const float* a3 = x3 ? x3 + (size_t)b * bs : nullptr;
-  for (int e = threadIdx.x; e < C * W; e += POST_BT) {
-    const int c = e / W, pcol = e % W;
-    const int t = t0 + pcol - padl;
-    float v = 0.f;
-    if (t >= 0 && t < L) {
-      const size_t off = (size_t)c * ld + t;
-      v = a1[off];
-      if (a2) v += a2[off];
-      if (a3) v += a3[off];
-      if (in_div != 1.f) v = v / in_div;
-      v = v > 0.f ? v : v * slope;
+  // one warp per channel row, lanes along time: coalesced, no index division, and the (up to 27) loads of a row are
+  // independent so that they are all in flight together
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int c = warp; c < C; c += POST_BT / 32) {
+    const size_t row = (size_t)c * ld;
+    float v[(POST_BT + POST_KMAX - 1 + 31) / 32];
+#pragma unroll
+    for (int i = 0; i < (POST_BT + POST_KMAX - 1 + 31) / 32; ++i) {
+      const int pcol = lane + 32 * i, t = t0 + pcol - padl;
+      float a = 0.f;
+      if (pcol < W && t >= 0 && t < L) {
+        a = a1[row + t];
+        if (a2) a += a2[row + t];
+        if (a3) a += a3[row + t];
+      }
+      v[i] = a;
     }
-    xs[c * W + pcol] = v;
+#pragma unroll
+    for (int i = 0; i < (POST_BT + POST_KMAX - 1 + 31) / 32; ++i) {
+      const int pcol = lane + 32 * i;
+      float a = v[i];
+      if (in_div != 1.f) a = a / in_div;
+      a = a > 0.f ? a : a * slope;
+      if (pcol < W) xs[c * W + pcol] = a;
+    }
   }
   for (int e = threadIdx.x; e < C * K; e += POST_BT) wsm[e] = w[e];
   __syncthreads();
@@ -620,8 +715,17 @@ __global__ void __launch_bounds__(POST_BT) conv_post_kernel(const float* __restr
   float av = 0.f;
   if (t < L) {
     float a = 0.f;
-    for (int c = 0; c < C; ++c)
-      for (int k = 0; k < K; ++k) a = fmaf(wsm[c * K + k], xs[c * W + threadIdx.x + k], a);
+    if (K == POST_KMAX) {  // every reference vocoder: same accumulation order, taps unrolled
+      for (int c = 0; c < C; ++c) {
+        const float* xr = xs + c * W + threadIdx.x;
+        const float* wr = wsm + c * POST_KMAX;
+#pragma unroll
+        for (int k = 0; k < POST_KMAX; ++k) a = fmaf(wr[k], xr[k], a);
+      }
+    } else {
+      for (int c = 0; c < C; ++c)
+        for (int k = 0; k < K; ++k) a = fmaf(wsm[c * K + k], xs[c * W + threadIdx.x + k], a);
+    }
     const float o = tanhf(a + bias[0]);
     pcm[(size_t)b * pcm_ld + t] = o;
     av = fabsf(o);

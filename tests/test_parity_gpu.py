@@ -89,7 +89,7 @@ def test_end_to_end_ids_to_pcm_contract(name):
     assert np.abs(audio.astype(np.int32) - g["audio"].astype(np.int32)).max() <= _i16_tol(ref, TOL_E2E)
 
 
-@pytest.mark.parametrize("n_ids,ls,noise", [(1, 1.0, 0.667), (2, 1.0, 0.0), (7, 1.5, 0.667), (64, 0.7, 0.3), (200, 1.0, 0.667)])
+@pytest.mark.parametrize("n_ids,ls,noise", [(1, 1.0, 0.667), (2, 1.0, 0.0), (7, 1.5, 0.667), (64, 0.7, 0.3), (200, 1.0, 0.667), (300, 1.0, 0.667)])
 def test_against_oracle(n_ids, ls, noise):
     ids = synth.bench_ids(n_ids, seed=100 + n_ids)
     eps = synth.seeded_eps(4096, seed=n_ids)

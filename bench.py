@@ -272,10 +272,11 @@ def run_extras(args, rank, world, local_rank, glow, voc, glue, hblob_factory, di
         if dist is not None:
             dist.barrier()
 
-    def timed(sched_list, rows_list):
+    def timed(sched_list, rows_list, warm_all=False):
         """rows_list[i] goes through sched_list[i]; returns (wall, utterances, frames) of this rank."""
         for sch, rows in zip(sched_list, rows_list):  # warm-up: arenas, attributes
-            sch.synthesize(rows[: min(len(rows), 2 * sch.max_batch)])
+            # ragged lengths: the longest bucket must have been seen, or its workspace growth (cudaFree + cudaMalloc) is timed
+            sch.synthesize(rows if warm_all else rows[: min(len(rows), 2 * sch.max_batch)])
         barrier()
         t0 = time.perf_counter()
         outs = []
@@ -327,7 +328,7 @@ def run_extras(args, rank, world, local_rank, glow, voc, glue, hblob_factory, di
         rows = [synth.bench_ids(int(n), seed=3000 + 97 * rank + i) for i, n in enumerate(rs.randint(64, 257, 128))]
         sch = BatchScheduler(glow, voc, glue, max_batch=32, max_cost=None, workers=2)
         try:
-            return timed([sch], [rows])
+            return timed([sch], [rows], warm_all=True)
         finally:
             sch.close()
 

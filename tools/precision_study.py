@@ -63,6 +63,7 @@ for act, wt, what in (("bf16x2", "bf16x2", "engine's scheme (3 products: hh + hl
                       ("fp16", "fp16x2", "ONE fp16 activation plane x split weights (2 products)"),
                       ("fp16", "fp32", "one fp16 activation plane, exact weights"),
                       ("fp16", "fp16", "fp16 activations and weights (1 product; the reference's `half`, fp32 accumulate)"),
+                      ("bf16x2", "fp16", "split activations x ONE fp16 weight plane (2 products)"),
                       ("bf16", "bf16x2", "one bf16 activation plane x split weights"),
                       ("bf16", "bf16", "plain bf16 (1 product)")):
     mx, rms = run(act, wt)

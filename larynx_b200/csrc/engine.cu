@@ -313,6 +313,7 @@ static void set_out(ConvParams& p, const Planes& pl, float slope, const Planes* 
 //   no_rbpair     HiFi-GAN ResBlock convs of the narrow stages as two launches instead of the fused kernel (rbpair_umma.cuh)
 //   stage_trace   per-item timeline of one CTA of every stage_umma launch on stderr (single-threaded use)
 //   no_stage_pair the 32-channel HiFi-GAN stage as one item per conv instead of one per ResBlock step (stage_pair_kernel)
+//   no_stage_stripe  stage kernels: every CTA gets a contiguous tile range of ONE branch per level instead of the striped order
 //   no_stage      HiFi-GAN ResBlock convs as one launch per conv position instead of one dataflow launch per stage (stage_umma.cuh)
 //   chain_trace   per-layer phase stamps of the persistent kernels on stderr
 //   trace         per-conv %globaltimer phase trace on stderr (single-threaded use; implies no_flow_chain)
@@ -1599,6 +1600,7 @@ int b200tts_call_create(int device, b200tts_call** out) {
   conv_umma_init_attributes();
   rbpair_umma_init_attributes();
   stage_umma_init_attributes();
+  stage_set_striped(!dbg_flag("no_stage_stripe"));
   attention_init_attributes();
   attn_umma_init_attributes();
   flow_chain_init_attributes();

@@ -16,6 +16,7 @@ bool rbpair_umma_supported(const ConvParams* c1, const ConvParams* c2, int n);
 int launch_rbpair_umma(const ConvParams* c1, const ConvParams* c2, int n, int batch, int Lmax, cudaStream_t stream);
 // all ResBlock convs of a HiFi-GAN stage in one persistent launch with tile-level dataflow (stage_umma.cu)
 void stage_umma_init_attributes();
+void stage_set_striped(bool on);  // item order of the stage kernels (stage_umma.cu); process-wide, set once at start-up
 bool stage_umma_supported(const ConvParams* convs, int n_levels, int n_cols);
 size_t stage_umma_table_bytes();
 int launch_stage_umma(const ConvParams* convs, int n_levels, int n_cols, int batch, const int* lens_h, void* tab_h, void* tab_d,

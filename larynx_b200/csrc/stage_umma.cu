@@ -54,7 +54,19 @@ static int resident_ctas(size_t smem) {
 struct StageStrip {
   int col, b, ntile, tiles;
   long long cost;
+  int t0 = 0;  // index of the strip's first tile
 };
+
+// Item order inside a level.  Contiguous ranges of ONE branch make a CTA's next level wait for the tile it has just issued (its
+// own neighbour in time): MMA + epilogue + publication of that tile = ~11 us of a 12.5 us item in profiles/r2d_stage_trace.log.
+// Striped: the tiles of a level are ordered (item, time tile, branch, n-tile) and cut into equal-cost ranges in THAT order, so a
+// CTA alternates between the branches and the tiles a next-level item needs from its own CTA were issued several items earlier;
+// the ones it needs from its neighbours are the last / first items of their ranges.  One segment per tile: used while the
+// segment table holds them (SG_MAX_SEGS), which covers single utterances and small batches — large batches have many tiles per
+// CTA and level, and the contiguous order (better weight reuse in L1/L2) loses nothing there.
+static bool g_striped = true;
+void stage_set_striped(bool on) { g_striped = on; }
+constexpr int SG_MAX_SEGS = 2048;
 int stage_partition(const StageStrip* strips, int n_strips, int nctas, int* seg_off, StageSeg* segs, int max_segs) {
   long long total = 0;
   for (int i = 0; i < n_strips; ++i) total += (long long)strips[i].tiles * strips[i].cost;
@@ -74,11 +86,11 @@ int stage_partition(const StageStrip* strips, int n_strips, int nctas, int* seg_
       }
       if (!open) {
         B2_CHECK(nseg < max_segs, "stage partition: too many segments");
-        segs[nseg].col = st.col; segs[nseg].b = st.b; segs[nseg].ntile = st.ntile; segs[nseg].t_begin = t; segs[nseg].t_end = t;
+        segs[nseg].col = st.col; segs[nseg].b = st.b; segs[nseg].ntile = st.ntile; segs[nseg].t_begin = st.t0 + t; segs[nseg].t_end = st.t0 + t;
         ++nseg;
         open = true;
       }
-      segs[nseg - 1].t_end = t + 1;
+      segs[nseg - 1].t_end = st.t0 + t + 1;
     }
   }
   for (int c = cur_cta + 1; c <= nctas; ++c) seg_off[c] = nseg;
@@ -169,11 +181,18 @@ int launch_stage_umma(const ConvParams* convs, int n_levels, int n_cols, int bat
   for (int lv = 0; lv < n_levels; ++lv)
     for (int j = 0; j < n_cols; ++j) dep_t[lv * n_cols + j] = lv > 0 ? (lv - 1) * n_cols + j : -1;
   std::vector<StageStrip> strips;
-  for (int j = 0; j < n_cols; ++j)
+  if (g_striped && n_tiles_all + nctas <= SG_MAX_SEGS) {
     for (int b = 0; b < batch; ++b)
-      for (int nt = 0; nt < ntiles; ++nt)
-        if (mtl[b] > 0) strips.push_back({j, b, nt, mtl[b], wcol[j]});
-  const int nseg = stage_partition(strips.data(), (int)strips.size(), nctas, off_t, seg_t, 2048);
+      for (int t = 0; t < mtl[b]; ++t)
+        for (int j = 0; j < n_cols; ++j)
+          for (int nt = 0; nt < ntiles; ++nt) strips.push_back({j, b, nt, 1, wcol[j], t});
+  } else {
+    for (int j = 0; j < n_cols; ++j)
+      for (int b = 0; b < batch; ++b)
+        for (int nt = 0; nt < ntiles; ++nt)
+          if (mtl[b] > 0) strips.push_back({j, b, nt, mtl[b], wcol[j]});
+  }
+  const int nseg = stage_partition(strips.data(), (int)strips.size(), nctas, off_t, seg_t, SG_MAX_SEGS);
   char* td = reinterpret_cast<char*>(tab_d);
   // only the bytes in use: conv table + dep + offsets + the segments actually written (~10 of 52 KB)
   B2_CUDA(cudaMemcpyAsync(td, th, (size_t)(reinterpret_cast<char*>(seg_t + nseg) - th), cudaMemcpyHostToDevice, s));
@@ -305,10 +324,17 @@ int launch_stage_pair(const ConvParams* c1, const ConvParams* c2, int n_levels, 
   for (int lv = 0; lv < n_levels; ++lv)
     for (int j = 0; j < n_cols; ++j) dep_t[lv * n_cols + j] = lv > 0 ? (lv - 1) * n_cols + j : -1;
   std::vector<StageStrip> strips;
-  for (int j = 0; j < n_cols; ++j)
+  if (g_striped && n_tiles_all + nctas <= SG_MAX_SEGS) {  // (the branches' tile strides differ by a few rows: same index ~ same time)
     for (int b = 0; b < batch; ++b)
-      if (mtl[(size_t)b * n_cols + j] > 0) strips.push_back({j, b, 0, mtl[(size_t)b * n_cols + j], wcol[j]});
-  const int nseg = stage_partition(strips.data(), (int)strips.size(), nctas, off_t, seg_t, 2048);
+      for (int t = 0; t < tiles_max; ++t)
+        for (int j = 0; j < n_cols; ++j)
+          if (t < mtl[(size_t)b * n_cols + j]) strips.push_back({j, b, 0, 1, wcol[j], t});
+  } else {
+    for (int j = 0; j < n_cols; ++j)
+      for (int b = 0; b < batch; ++b)
+        if (mtl[(size_t)b * n_cols + j] > 0) strips.push_back({j, b, 0, mtl[(size_t)b * n_cols + j], wcol[j]});
+  }
+  const int nseg = stage_partition(strips.data(), (int)strips.size(), nctas, off_t, seg_t, SG_MAX_SEGS);
   char* td = reinterpret_cast<char*>(tab_d);
   // only the bytes in use: conv table + dep + offsets + the segments actually written (~10 of 52 KB)
   B2_CUDA(cudaMemcpyAsync(td, th, (size_t)(reinterpret_cast<char*>(seg_t + nseg) - th), cudaMemcpyHostToDevice, s));

@@ -516,7 +516,8 @@ def test_simt_reference_path_still_matches():
 def test_vocoder_launch_schemes_agree_bit_for_bit():
     """The HiFi-GAN ResBlocks run as one dataflow launch per stage (stage_umma.cuh, the default; the 32-channel stage with a
     whole ResBlock step per item unless no_stage_pair), as fused c1->c2 steps for the narrow stages (rbpair_umma.cuh,
-    B200TTS_DEBUG=no_stage) or as one launch per conv position (no_stage,no_rbpair).  All of them
+    B200TTS_DEBUG=no_stage) or as one launch per conv position (no_stage,no_rbpair), and the stage kernels cut their tiles into
+    per-CTA ranges in striped or (no_stage_stripe) contiguous order.  All of them
     execute the same MMAs in the same order with the same epilogue arithmetic: the waveforms must be identical, for a single
     utterance and for a ragged batch (different tile ranges per item, tiles that end inside a 128-row block)."""
     import subprocess
@@ -544,12 +545,12 @@ v.model.infer(call, batch, np.array(lens, np.int32), 3, T, many, None, T * hop)
 np.savez(sys.argv[1], one=one, many=many)
 """
     outs = {}
-    for mode in ("", "no_stage_pair", "no_stage", "no_stage,no_rbpair"):
+    for mode in ("", "no_stage_stripe", "no_stage_pair", "no_stage", "no_stage,no_rbpair"):
         f = os.path.join(tempfile.mkdtemp(), "o.npz")
         subprocess.run([sys.executable, "-c", code, f], check=True, env=dict(os.environ, B200TTS_DEBUG=mode),
                        cwd=os.path.dirname(os.path.dirname(__file__)))
         outs[mode] = np.load(f)
-    for mode in ("no_stage_pair", "no_stage", "no_stage,no_rbpair"):
+    for mode in ("no_stage_stripe", "no_stage_pair", "no_stage", "no_stage,no_rbpair"):
         assert np.array_equal(outs[""]["one"], outs[mode]["one"]), mode
         assert np.array_equal(outs[""]["many"], outs[mode]["many"]), mode
     many = outs[""]["many"]

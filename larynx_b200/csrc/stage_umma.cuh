@@ -46,13 +46,17 @@ struct StageParams {
 constexpr int SG_EW = 16;
 
 #ifndef SG_WST1
-#define SG_WST1 8  // weight ring slots (16 KB) of the 128-channel-tile variant
+#define SG_WST1 6  // weight ring slots (16 KB) of the 128-channel-tile variant
+#endif
+#ifndef SG_AST1
+#define SG_AST1 4  // activation ring stages (one 32-channel chunk, 26.6 KB) of the 128-channel-tile variant: a whole item of the
+                   // 128-channel stage; 4 + 6 slots measured 1 % faster than 2 + 8 (profiles/r2d_notes.md)
 #endif
 
 template <int MT>
 struct StageCfg {  // ring geometry per tile height (the persistent variants of conv_umma.cu)
   static constexpr int WST = MT == 1 ? SG_WST1 : (MT == 2 ? 6 : 3);
-  static constexpr int AST = 2;
+  static constexpr int AST = MT == 1 ? SG_AST1 : 2;
   static constexpr int G = MT == 1 ? 1 : (MT == 2 ? 2 : 4);
   static constexpr int RA = MT * 128 + UM_HALO;
   static size_t smem_bytes(int NT, int Cout) {
@@ -101,16 +105,16 @@ __global__ void __launch_bounds__(SG_EW * 32 + 128, 1) stage_umma_kernel(const _
   unsigned char* sA = smem_raw;
   unsigned char* sW = smem_raw + AST * a_stage;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sW + WST * w_ring);
-  uint64_t* a_full = bars;          // [AST]
-  uint64_t* a_empty = bars + 2;     // [AST]
-  uint64_t* w_full = bars + 4;      // [WST <= 9]
-  uint64_t* w_empty = bars + 13;    // [WST <= 9]
-  uint64_t* acc_full = bars + 22;   // [2]
-  uint64_t* acc_empty = bars + 24;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
-  unsigned int* s_done = reinterpret_cast<unsigned int*>(bars + 27);  // epilogue warps that have finished an item (monotonic)
-  static_assert(WST <= 9 && AST == 2, "barrier slots");
-  float* s_bias_all = reinterpret_cast<float*>(bars + 28);  // [n_convs][Cout]
+  uint64_t* a_full = bars;          // [AST <= 4]
+  uint64_t* a_empty = bars + 4;     // [AST <= 4]
+  uint64_t* w_full = bars + 8;      // [WST <= 9]
+  uint64_t* w_empty = bars + 17;    // [WST <= 9]
+  uint64_t* acc_full = bars + 26;   // [2]
+  uint64_t* acc_empty = bars + 28;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
+  unsigned int* s_done = reinterpret_cast<unsigned int*>(bars + 31);  // epilogue warps that have finished an item (monotonic)
+  static_assert(WST <= 9 && AST <= 4, "barrier slots");
+  float* s_bias_all = reinterpret_cast<float*>(bars + 32);  // [n_convs][Cout]
   const float *s_inv = nullptr, *s_anb = nullptr, *s_ans = nullptr;  // named by the (dead here) coupling branch of the epilogue text
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;

@@ -275,7 +275,9 @@ def run_extras(args, rank, world, local_rank, glow, voc, glue, hblob_factory, di
     def timed(sched_list, rows_list, warm_all=False):
         """rows_list[i] goes through sched_list[i]; returns (wall, utterances, frames) of this rank."""
         for sch, rows in zip(sched_list, rows_list):  # warm-up: arenas, attributes
-            # ragged lengths: the longest bucket must have been seen, or its workspace growth (cudaFree + cudaMalloc) is timed
+            # ragged lengths: every worker must have seen the longest bucket, or its workspace growth (cudaFree + cudaMalloc) is timed
+            if warm_all:
+                sch.reserve(rows)
             sch.synthesize(rows if warm_all else rows[: min(len(rows), 2 * sch.max_batch)])
         barrier()
         t0 = time.perf_counter()

@@ -213,7 +213,6 @@ __global__ void __launch_bounds__(SG_EW * 32 + 128, 1) stage_umma_kernel(const _
       const long long row0 = (long long)mtile * (MT * 128) - p.pad_left + UM_PADL;
       issue_a_chunks<NSPLIT, AST>(lane, as, aph, nch, a_empty, a_full, sA, a_stage, a_split_bytes, RA, xp, p.xp_kc, p.xp_rows, row0,
                                   MT * 128 + (p.K - 1) * p.dil);
-      if (lane == 0) SG_TRACE(ita, 2);
       ++ita;
     });
   } else if (warp == W_MMA) {
@@ -245,7 +244,7 @@ __global__ void __launch_bounds__(SG_EW * 32 + 128, 1) stage_umma_kernel(const _
         for (int k0 = 0; k0 < K; k0 += G) {
           mbar_wait(&w_full[ws], wph);
           tc_fence_after();
-          if (c == 0 && k0 == 0 && lane == 0) SG_TRACE(it, 2);  // (the activation warp's stamp 2 of this item is overwritten: debug only)
+          if (c == 0 && k0 == 0 && lane == 0) SG_TRACE(it, 2);
           const int cnt = min(G, K - k0);
           if (elect_one()) {
             for (int kk = 0; kk < cnt; ++kk) {

@@ -81,8 +81,41 @@ class BatchScheduler:
             job = self._jobs.get()
             if job is None:
                 return
+            if callable(job):
+                job()
+                continue
             req, k = job
             req.run(k, self._synth)
+
+    def reserve(self, id_rows: Sequence[np.ndarray]):
+        """Size every worker's workspaces for a request like `id_rows` before it matters: each worker runs the costliest
+        micro-batch of the plan once (results dropped).  Which worker picks which micro-batch is not deterministic, so
+        without this the first long micro-batch a worker meets grows its arenas (cudaFree + cudaMalloc of gigabytes: tens of
+        milliseconds and a device-wide sync that also stalls the other workers) — seen as a 2x swing of the batch-32
+        throughput from run to run.  A serving process calls it once at start-up with its longest expected request."""
+        assert not self._closed, "scheduler is closed"
+        rows = [np.asarray(r, dtype=np.int64).reshape(-1) for r in id_rows]
+        plan = self.plan(rows)
+        if not plan:
+            return
+        big = max(plan, key=lambda idx: len(idx) * max(len(rows[i]) for i in idx))
+        batch = [rows[i] for i in big]
+        gate = threading.Barrier(self.workers + 1)
+        errors: List[BaseException] = []
+
+        def job():
+            try:
+                self._synth(batch, 0)
+            except BaseException as e:  # noqa: BLE001 - re-raised on the caller's thread
+                errors.append(e)
+            finally:
+                gate.wait()  # nobody takes a second job before every worker has had its one
+
+        for _ in range(self.workers):
+            self._jobs.put(job)
+        gate.wait()
+        if errors:
+            raise errors[0]
 
     # ------------------------------------------------------------------------------------------------------------
     def plan(self, id_rows: Sequence[np.ndarray]) -> List[List[int]]:

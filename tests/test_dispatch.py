@@ -2,6 +2,7 @@
 import os
 import socket
 
+import pytest
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -110,3 +111,37 @@ def test_batch_scheduler_orders_results_and_propagates_errors():
         BatchScheduler(max_batch=4, workers=2, synth=broken).synthesize(rows)
     with pytest.raises(ValueError):
         list(BatchScheduler(max_batch=4, workers=2, synth=broken).stream(rows))
+
+
+def test_scheduler_reserve_runs_the_costliest_batch_once_on_every_worker():
+    import threading
+
+    from larynx_b200.scheduler import BatchScheduler
+
+    seen = []
+    lock = threading.Lock()
+
+    def fake(rows, seed):
+        with lock:
+            seen.append((threading.get_ident(), sum(len(r) for r in rows), len(rows)))
+        return [np.zeros(len(r), np.int16) for r in rows]
+
+    sch = BatchScheduler(max_batch=4, max_cost=None, workers=3, synth=fake)
+    try:
+        rows = [np.ones(n, np.int64) for n in (3, 50, 7, 48, 2, 49, 51, 9, 1)]
+        sch.reserve(rows)
+        assert len(seen) == 3 and len({t for t, _, _ in seen}) == 3  # one job per worker thread
+        assert all(total == 9 + 48 + 49 + 50 and n == 4 for _, total, n in seen)  # ... the costliest micro-batch (4 x 50 padded)
+        out = sch.synthesize(rows)  # the scheduler still works afterwards
+        assert [len(a) for a in out] == [len(r) for r in rows]
+        sch.reserve([])  # nothing to plan: no-op
+
+        def broken(rows, seed):
+            raise ValueError("boom")
+
+        bad = BatchScheduler(max_batch=2, workers=2, synth=broken)
+        with pytest.raises(ValueError):
+            bad.reserve(rows)
+        bad.close()
+    finally:
+        sch.close()

@@ -1,6 +1,7 @@
 """Drop-in for `larynx.glow_tts.GlowTextToSpeech` (larynx/glow_tts.py:29-170) on libb200tts.
 
-Same constructor (a TextToSpeechModelConfig whose model_path holds `generator.pth` + `config.json`),
+Same constructor (a TextToSpeechModelConfig whose model_path holds `config.json` + `generator.pth`, or `generator.onnx` whose
+initializers kept their parameter names: pack.pack_from_directory),
 same `phonemes_to_mels(phoneme_ids, settings)` contract: int64 ids [T_x] in, float32 mel
 [1, 80, T_y] numpy array out (what the ONNX backend returns, larynx/glow_tts.py:161-170), same
 settings keys (`noise_scale` 0.667, `length_scale` 1.0; larynx/glow_tts.py:104-121).
@@ -43,14 +44,8 @@ class GlowTextToSpeech(TextToSpeechModel):
                 model_config = json.load(f)
         self.config = model_config
         if blob is None:
-            pytorch_path = model_path / "generator.pth"
-            if not pytorch_path.is_file():
-                raise FileNotFoundError(
-                    f"{pytorch_path} not found: larynx_b200 reads the PyTorch checkpoint of a voice "
-                    "(generator.onnx alone cannot be read without the onnx package)"
-                )
-            _LOGGER.debug("Packing GlowTTS weights from %s", pytorch_path)
-            blob = pack.pack_glow(pack.load_state_dict(pytorch_path, "model"), model_config)
+            _LOGGER.debug("Packing GlowTTS weights from %s", model_path)
+            blob = pack.pack_from_directory(model_path, "model", model_config, pack.pack_glow)
         self.model = GlowModel(blob, self.device)
         self.noise_scale = 0.667
         self.length_scale = 1.0

@@ -38,11 +38,8 @@ class HiFiGanVocoder(VocoderModel):
                 model_config = json.load(f)
         self.config = model_config
         if blob is None:
-            pytorch_path = model_path / "generator.pth"
-            if not pytorch_path.is_file():
-                raise FileNotFoundError(f"{pytorch_path} not found: larynx_b200 reads the PyTorch checkpoint of a vocoder")
-            _LOGGER.debug("Packing HiFi-GAN weights from %s", pytorch_path)
-            blob = pack.pack_hifigan(pack.load_state_dict(pytorch_path, "generator"), _effective_config(model_config))
+            _LOGGER.debug("Packing HiFi-GAN weights from %s", model_path)
+            blob = pack.pack_from_directory(model_path, "generator", _effective_config(model_config), pack.pack_hifigan)
         self.model = HifiGanModel(blob, self.device)
         self.mel_channels = self.model.mel_channels
         self.denoiser_strength = float(getattr(config, "denoiser_strength", 0.0) or 0.0) if config is not None else 0.0

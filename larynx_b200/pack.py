@@ -346,3 +346,33 @@ def load_state_dict(path, key: str) -> Dict[str, np.ndarray]:
         raise KeyError(f"Missing '{key}' in state dict")
     sd = ckpt[key]
     return {(k[7:] if k.startswith("module.") else k): v.detach().cpu().float().numpy() for k, v in sd.items()}
+
+
+def load_voice_weights(model_dir, key: str) -> Tuple[Dict[str, np.ndarray], str]:
+    """The weights of a voice / vocoder directory: `generator.pth` (the reference's PyTorch backend, larynx/glow_tts.py:66-84,
+    larynx/hifi_gan.py:70-99) when it exists, else the initializers of `generator.onnx` (what released voices ship) read by
+    name (onnx_weights.py).  Returns (state dict, the file it came from)."""
+    from pathlib import Path
+
+    d = Path(model_dir)
+    pth, onx = d / "generator.pth", d / "generator.onnx"
+    if pth.is_file():
+        return load_state_dict(pth, key), str(pth)
+    if onx.is_file():
+        from . import onnx_weights
+
+        return onnx_weights.state_dict(onx), str(onx)
+    raise FileNotFoundError(f"neither {pth} nor {onx} exists")
+
+
+def pack_from_directory(model_dir, key: str, config: dict, packer) -> np.ndarray:
+    """packer(state dict, config) on the directory's weights; a graph whose export folded parameters into anonymous
+    constants (so that names the packer needs are gone) fails with those names."""
+    sd, src = load_voice_weights(model_dir, key)
+    try:
+        return packer(sd, config)
+    except KeyError as e:
+        if src.endswith(".onnx"):
+            raise KeyError(f"{src}: no initializer named {e} — this export folded the parameter into an anonymous constant; "
+                           "larynx_b200 reads ONNX weights by parameter name only (use the voice's generator.pth)") from e
+        raise

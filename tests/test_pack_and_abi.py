@@ -3,6 +3,7 @@ import ctypes
 import os
 import re
 
+import pytest
 import numpy as np
 import torch
 import torch.nn.functional as F
@@ -202,3 +203,87 @@ def test_stage_partition_is_contiguous_and_balanced(built_library):
         if int(np.sum(tiles)) >= 4 * nctas:  # enough tiles per CTA for a meaningful lower bound
             assert busy.min() >= mean - per_tile.max() - 1 and len(busy) == nctas
         assert n_ranges >= len(busy) and n_ranges <= len(busy) + len(tiles)
+
+
+# ---- ONNX initializers without the onnx package (larynx_b200/onnx_weights.py) -------------------------------------
+def _pb_varint(x: int) -> bytes:
+    x &= (1 << 64) - 1  # negative int64 values travel as their two's complement (10 bytes)
+    out = bytearray()
+    while True:
+        b = x & 0x7F
+        x >>= 7
+        out.append(b | (0x80 if x else 0))
+        if not x:
+            return bytes(out)
+
+
+def _pb_field(no: int, payload: bytes) -> bytes:  # length-delimited
+    return _pb_varint((no << 3) | 2) + _pb_varint(len(payload)) + payload
+
+
+def _onnx_tensor(name: str, a: np.ndarray, style: str) -> bytes:
+    """TensorProto in one of the encodings exporters use: raw_data, packed float_data, one float_data entry per element."""
+    t = b"".join(_pb_varint((1 << 3) | 0) + _pb_varint(int(d)) for d in a.shape) if style != "packed_dims" else \
+        _pb_field(1, b"".join(_pb_varint(int(d)) for d in a.shape))
+    t += _pb_varint((2 << 3) | 0) + _pb_varint(1)  # FLOAT
+    t += _pb_field(8, name.encode())
+    flat = np.ascontiguousarray(a, dtype="<f4").reshape(-1)
+    if style == "unpacked_floats":
+        t += b"".join(_pb_varint((4 << 3) | 5) + flat[i : i + 1].tobytes() for i in range(flat.size))
+    elif style == "packed_floats":
+        t += _pb_field(4, flat.tobytes())
+    else:
+        t += _pb_field(9, flat.tobytes())
+    return t
+
+
+def _onnx_model(tensors, extra_int64=None) -> bytes:
+    graph = _pb_field(2, b"torch_jit")
+    node = _pb_field(4, b"Conv") + _pb_field(1, b"x") + _pb_field(2, b"y")
+    graph = _pb_field(1, node) + graph
+    styles = ["raw", "packed_floats", "packed_dims", "unpacked_floats"]
+    for i, (k, a) in enumerate(tensors.items()):
+        graph += _pb_field(5, _onnx_tensor(k, a, styles[i % 4] if a.size <= 64 else styles[i % 3]))
+    if extra_int64 is not None:  # shape constants live among the initializers too
+        t = _pb_varint((1 << 3) | 0) + _pb_varint(len(extra_int64)) + _pb_varint((2 << 3) | 0) + _pb_varint(7) + _pb_field(8, b"onnx::Reshape_7")
+        t += _pb_field(7, b"".join(_pb_varint(int(v)) for v in extra_int64))
+        graph += _pb_field(5, t)
+    return _pb_varint((1 << 3) | 0) + _pb_varint(7) + _pb_field(2, b"pytorch") + _pb_field(7, graph) + _pb_field(8, _pb_varint((2 << 3) | 0) + _pb_varint(11))
+
+
+def test_onnx_initializers_are_read_by_name_and_pack_like_the_checkpoint(tmp_path):
+    """A vocoder directory that holds only generator.onnx (what released voices ship): the initializers — named like the
+    parameters after remove_weight_norm(), hifi_gan/models.py:204-211 — pack to the same blob as the generator.pth of the same
+    weights; an export that lost a parameter name fails with that name."""
+    from larynx_b200 import onnx_weights, pack, synth
+
+    cfg = synth.hifigan_config("vctk_small")
+    sd = synth.hifigan_state_dict(cfg, 7)
+    folded = {}
+    for k in sd:
+        if k.endswith(".weight_g"):
+            folded[k[: -len("_g")]] = pack.fold_weight_norm(sd, k[: -len(".weight_g")])
+        elif not k.endswith(".weight_v"):
+            folded[k] = pack._np(sd[k])
+    d = tmp_path / "voc"
+    d.mkdir()
+    (d / "generator.onnx").write_bytes(_onnx_model({"module." + k if i % 5 == 0 else k: v for i, (k, v) in enumerate(folded.items())},
+                                                   extra_int64=[1, -1, 80]))
+    ini = onnx_weights.read_initializers(d / "generator.onnx")
+    assert ini["onnx::Reshape_7"].dtype == np.int64 and ini["onnx::Reshape_7"].tolist() == [1, -1, 80]
+    got = onnx_weights.state_dict(d / "generator.onnx")
+    assert set(got) == set(folded)  # float tensors only, `module.` stripped
+    for k, v in folded.items():
+        assert got[k].dtype == np.float32 and got[k].shape == v.shape and np.array_equal(got[k], v), k
+    blob = pack.pack_from_directory(d, "generator", cfg, pack.pack_hifigan)
+    assert np.array_equal(blob, pack.pack_hifigan(sd, cfg))
+
+    broken = {k: v for k, v in folded.items() if k != "conv_post.bias"}
+    (d / "generator.onnx").write_bytes(_onnx_model(broken))
+    with pytest.raises(KeyError, match="conv_post.bias"):
+        pack.pack_from_directory(d, "generator", cfg, pack.pack_hifigan)
+    with pytest.raises(FileNotFoundError):
+        pack.pack_from_directory(tmp_path / "nothing", "generator", cfg, pack.pack_hifigan)
+    (d / "generator.onnx").write_bytes(b"\x08\x07")  # a model without a graph
+    with pytest.raises(ValueError):
+        onnx_weights.read_initializers(d / "generator.onnx")

@@ -20,6 +20,8 @@ from __future__ import annotations
 import struct
 from typing import Optional, Dict, List, Tuple
 
+import json
+
 import numpy as np
 
 MAGIC = b"B2TTSBLB"
@@ -283,7 +285,10 @@ def pack_glow(sd: Dict[str, np.ndarray], config: dict, simt: Optional[bool] = No
                         g(p + f".wn.res_skip_layers.{l}.bias"))
         w, bias = interleave_halves(g(p + ".end.weight"), g(p + ".end.bias"))
         bw.add_conv(f"flow{b}.end", w, bias)
-        winv = np.linalg.inv(g(f"decoder.flows.{inv}.weight").astype(np.float32)).astype(np.float32)
+        if f"decoder.flows.{inv}.weight_inv" in sd:  # an ONNX export carries the matrix of store_inverse() itself
+            winv = g(f"decoder.flows.{inv}.weight_inv").reshape(m["n_split"], m["n_split"])
+        else:
+            winv = np.linalg.inv(g(f"decoder.flows.{inv}.weight").astype(np.float32)).astype(np.float32)
         bw.add(f"flow{b}.inv", winv)
         bw.add(f"flow{b}.an_bias", g(f"decoder.flows.{a}.bias").reshape(-1))
         bw.add(f"flow{b}.an_scale", np.exp(-g(f"decoder.flows.{a}.logs").reshape(-1)).astype(np.float32))
@@ -361,6 +366,9 @@ def load_voice_weights(model_dir, key: str) -> Tuple[Dict[str, np.ndarray], str]
     if onx.is_file():
         from . import onnx_weights
 
+        if key == "model":  # GlowTTS: some parameters only survive as anonymous constants (onnx_weights.glow_state_dict)
+            with open(d / "config.json", "r", encoding="utf-8") as f:
+                return onnx_weights.glow_state_dict(onx, json.load(f)), str(onx)
         return onnx_weights.state_dict(onx), str(onx)
     raise FileNotFoundError(f"neither {pth} nor {onx} exists")
 

@@ -287,3 +287,52 @@ def test_onnx_initializers_are_read_by_name_and_pack_like_the_checkpoint(tmp_pat
     (d / "generator.onnx").write_bytes(b"\x08\x07")  # a model without a graph
     with pytest.raises(ValueError):
         onnx_weights.read_initializers(d / "generator.onnx")
+
+
+def _fold_all(sd):
+    from larynx_b200 import pack
+
+    out = {}
+    for k in sd:
+        if k.endswith(".weight_g"):
+            out[k[: -len("_g")]] = pack.fold_weight_norm(sd, k[: -len(".weight_g")])
+        elif not k.endswith(".weight_v"):
+            out[k] = pack._np(sd[k])
+    return out
+
+
+def test_torch_exports_of_the_reference_modules_are_read_back():
+    """tests/golden/{glow_tiny,hifigan_tiny}.onnx are the reference's own modules traced by torch's ONNX exporter
+    (oracle/make_onnx_fixture.py).  HiFi-GAN keeps every parameter name.  GlowTTS loses the LayerNorm scales/shifts, ActNorm
+    logs, the weight-normed `start` convs and the inverted 1x1 matrices to anonymous constants: onnx_weights.glow_state_dict
+    recovers them from the execution order — every tensor must equal the checkpoint the export was made from."""
+    from larynx_b200 import onnx_weights, synth
+    from oracle import make_onnx_fixture as fx
+
+    golden = os.path.join(os.path.dirname(__file__), "golden")
+    hcfg = fx.hifigan_tiny_config()
+    want = _fold_all(synth.hifigan_state_dict(hcfg, fx.HIFI_SEED))
+    got = onnx_weights.state_dict(os.path.join(golden, "hifigan_tiny.onnx"))
+    assert set(got) == set(want)
+    for k, v in want.items():
+        assert got[k].shape == v.shape and np.abs(got[k] - v).max() <= 1e-6 * max(1.0, float(np.abs(v).max())), k
+
+    gcfg = fx.glow_tiny_config()
+    truth = synth.glow_state_dict(gcfg, fx.GLOW_SEED)
+    got = onnx_weights.glow_state_dict(os.path.join(golden, "glow_tiny.onnx"), gcfg)
+    want = _fold_all(truth)
+    n_inv = 0
+    for k, v in want.items():
+        if k.endswith(".weight") and v.shape == (4, 4):  # InvConvNear: the export carries store_inverse()'s matrix
+            assert k not in got
+            g, v = got[k + "_inv"], np.linalg.inv(v.astype(np.float64)).astype(np.float32)
+            n_inv += 1
+        else:
+            g = got[k]
+        assert g.shape == v.shape or g.size == v.size, k
+        assert np.abs(g.reshape(-1) - v.reshape(-1)).max() <= 2e-6 * max(1.0, float(np.abs(v).max())), k
+    assert n_inv == gcfg["model"]["n_blocks_dec"]
+    assert set(got) == {k + "_inv" if (k.endswith(".weight") and want[k].shape == (4, 4)) else k for k in want}
+    # a graph that is not a GlowTTS export is refused, not guessed at
+    with pytest.raises(ValueError):
+        onnx_weights.glow_state_dict(os.path.join(golden, "hifigan_tiny.onnx"), gcfg)
